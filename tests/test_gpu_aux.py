@@ -1,0 +1,29 @@
+"""GPU parity of the callers either side of the path: push_delta and align."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_push_delta(vcb, oracle):
+    rng = np.random.default_rng(2)
+    lens = [1, 2, 3, 50, 7]
+    off = np.concatenate([[0], np.cumsum(lens)])
+    src = rng.standard_normal((5, off[-1]))
+    out = vcb.push_delta(src, off)
+    ref = np.concatenate([oracle.push_delta(np.asfortranarray(src[:, off[i]:off[i + 1]])) for i in range(5)], 1)
+    assert np.array_equal(out, ref)
+    assert np.array_equal(vcb.push_delta(src[:, :50]), oracle.push_delta(np.asfortranarray(src[:, :50])))
+
+
+def test_align(vcb, oracle):
+    tm, to, sq, so = vcb.synth.dtw_pairs(7, 12, (60, 120), 5, noise=0.1)
+    newtgt, paths = vcb.align_batch(tm, to, sq, so)
+    for p in range(7):
+        s, nt, path = oracle.align(np.asfortranarray(tm[:, to[p]:to[p + 1]]), np.asfortranarray(sq[:, so[p]:so[p + 1]]))
+        assert np.array_equal(paths[so[p]:so[p + 1]], path)
+        assert np.array_equal(newtgt[:, to[p]:to[p + 1]], nt)
+    s, nt = vcb.align(tm[:, :to[1]], sq[:, :so[1]])
+    assert np.array_equal(nt, newtgt[:, :to[1]])
+    with pytest.raises(vcb.DimensionMismatch):
+        vcb.align(np.zeros((3, 4)), np.zeros((2, 4)))                 # src/align.jl:11-13

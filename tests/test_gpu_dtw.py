@@ -1,0 +1,112 @@
+"""GPU parity: DTW paths must be bit-exact with the oracle (reference src/dtw.jl)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def test_reference_known_answers(vcb):
+    for c in json.load(open(os.path.join(GOLDEN, "dtw_reference_tests.json"))):
+        d = vcb.DTWs.DTW(bstep=c["bstep"], fstep=c["fstep"])
+        p = vcb.DTWs.fit(d, np.array(c["template"], float).T, np.array(c["sequence"], float).T)
+        assert p.tolist() == c["expected"]
+
+
+def test_golden_random_pairs(vcb):
+    z = np.load(os.path.join(GOLDEN, "dtw_random.npz"))
+    for fs, bs in [(0, 1), (0, 2), (1, 2), (0, 5), (3, 20)]:       # 2-, 4- and 8-bit back-pointer builds
+        paths, fc = vcb.DTWs.fit_batch(vcb.DTWs.DTW(fstep=fs, bstep=bs), z["tmpl"], z["tmpl_off"], z["seq"], z["seq_off"])
+        assert np.array_equal(paths, z[f"paths_f{fs}_b{bs}"]), (fs, bs)
+        assert np.array_equal(fc, z[f"cost_f{fs}_b{bs}"]), (fs, bs)
+
+
+@pytest.mark.parametrize("fstep,bstep", [(0, 2), (0, 1)])
+def test_c3_shaped_pairs_bit_exact(vcb, oracle, fstep, bstep):
+    tm, to, sq, so = vcb.synth.dtw_pairs(24, 24, (550, 650), 1003)
+    paths, fc = vcb.DTWs.fit_batch(vcb.DTWs.DTW(fstep=fstep, bstep=bstep), tm, to, sq, so)
+    ref, rfc = oracle.dtw_fit_batch(tm, to, sq, so, fstep, bstep, nthreads=oracle.max_threads())
+    assert np.array_equal(paths, ref)
+    assert np.array_equal(fc, rfc)
+
+
+def test_ragged_and_tiny(vcb, oracle):
+    rng = np.random.default_rng(4)
+    S = [1, 2, 31, 32, 33, 97, 1000, 1024]
+    T = [1, 5, 16, 17, 15, 200, 37, 3]
+    to = np.concatenate([[0], np.cumsum(S)]); so = np.concatenate([[0], np.cumsum(T)])
+    tm = rng.standard_normal((3, to[-1])); sq = rng.standard_normal((3, so[-1]))
+    for fs, bs in [(0, 1), (0, 2), (2, 2)]:
+        paths, fc = vcb.DTWs.fit_batch(vcb.DTWs.DTW(fstep=fs, bstep=bs), tm, to, sq, so)
+        ref, rfc = oracle.dtw_fit_batch(tm, to, sq, so, fs, bs)
+        assert np.array_equal(paths, ref) and np.array_equal(fc, rfc)
+
+
+def test_ties_follow_reference_order(vcb, oracle):
+    # integer-valued features produce many exact ties: candidate order and strict '<' matter
+    rng = np.random.default_rng(9)
+    tm = rng.integers(0, 3, size=(2, 80)).astype(float); sq = rng.integers(0, 3, size=(2, 90)).astype(float)
+    for fs, bs in [(0, 1), (0, 2), (1, 3)]:
+        p = vcb.DTWs.fit(vcb.DTWs.DTW(fstep=fs, bstep=bs), tm, sq)
+        assert np.array_equal(p, oracle.DTW(fstep=fs, bstep=bs).fit(tm, sq))
+
+
+def test_online_update(vcb, oracle):
+    rng = np.random.default_rng(12)
+    tm, sq = rng.standard_normal((6, 40)), rng.standard_normal((6, 25))
+    d = vcb.DTWs.DTW(fstep=0, bstep=2)
+    vcb.DTWs.set_template(d, tm)
+    for t in range(25):
+        vcb.DTWs.update(d, sq[:, t])
+    o = oracle.DTW(fstep=0, bstep=2); ref = o.fit(tm, sq)
+    c, b = o.tables()
+    assert np.array_equal(d.costtable, c) and np.array_equal(d.backpointer, b)
+    assert np.array_equal(vcb.DTWs.backward(d), ref)
+
+
+def test_device_entry_point(vcb, oracle):
+    import torch
+    tm, to, sq, so = vcb.synth.dtw_pairs(5, 24, (100, 140), 77)
+    dt = torch.from_numpy(np.ascontiguousarray(tm.T)).cuda(); ds = torch.from_numpy(np.ascontiguousarray(sq.T)).cuda()
+    paths, fc = vcb.DTWs.fit_batch(vcb.DTWs.DTW(fstep=0, bstep=2), dt, to, ds, so)
+    torch.cuda.synchronize()
+    ref, rfc = oracle.dtw_fit_batch(tm, to, sq, so, 0, 2)
+    assert np.array_equal(paths.cpu().numpy(), ref) and np.array_equal(fc.cpu().numpy(), rfc)
+
+
+def test_full_c3_properties(vcb):
+    """BASELINE C3 at full size (1000 pairs): properties that need no oracle run."""
+    tm, to, sq, so = vcb.synth.config_c3(1000)
+    paths, fc = vcb.DTWs.fit_batch(vcb.DTWs.DTW(fstep=0, bstep=2), tm, to, sq, so)
+    for p in range(0, 1000, 37):
+        path = paths[so[p]:so[p + 1]]
+        S = to[p + 1] - to[p]
+        step = np.diff(path)
+        assert path.min() >= 1 and path.max() <= S and step.min() >= 0 and step.max() <= 2
+        # the accumulated cost along the returned path equals the reported final cost
+        t_ = tm[:, to[p]:to[p + 1]]; s_ = sq[:, so[p]:so[p + 1]]
+        # first frame: best predecessor in the initial column (cost[:,1] = 1:S); afterwards the
+        # predecessor is the previous path state
+        prev_candidates = np.arange(1, S + 1, dtype=float)
+        total = None
+        for t in range(len(path)):
+            i = path[t]
+            oc = 0.0
+            for k in range(24):
+                dlt = s_[k, t] - t_[k, i - 1]
+                oc = oc + dlt * dlt
+            if t == 0:
+                best = prev_candidates[i - 1] + oc + 1.0
+                for j in range(max(1, i - 2), i + 1):
+                    tr = 0.0 if i == j + 1 else (1.0 if i == j else 2.0)
+                    best = min(best, prev_candidates[j - 1] + oc + tr)
+                total = best
+            else:
+                j = path[t - 1]
+                tr = 0.0 if i == j + 1 else (1.0 if i == j else 2.0)
+                total = total + oc + tr
+        assert total == fc[p]

@@ -1,0 +1,654 @@
+// vcb_api.cu -- the C ABI of libvcb200.so (include/vcb200.h): argument checks, handle lifetime,
+// host<->device staging and kernel selection.  No exception leaves this file.
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+
+#include "vcb_kernels.h"
+
+namespace vcb {
+
+static thread_local std::string t_last_error;
+std::atomic<int64_t> g_launches{0};
+std::atomic<int> g_variant{0};
+
+int32_t fail(int32_t code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    t_last_error = buf;
+    return code;
+}
+
+// One-time per-device setup: require sm_100, keep the stream-ordered pool's memory.
+static int32_t ensure_device(int* dev_out = nullptr) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess)
+        return fail(VCB_ECUDA, "no CUDA device available (%s); libvcb200 has no CPU path", cudaGetErrorString(e));
+    static std::mutex mu;
+    static bool ready[64] = {false};
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev < 64 && !ready[dev]) {
+        cudaDeviceProp prop;
+        VCB_CUDA(cudaGetDeviceProperties(&prop, dev));
+        if (prop.major != 10)
+            return fail(VCB_ECUDA, "device %d (%s, sm_%d%d) is not a Blackwell sm_100 GPU; libvcb200 is built for sm_100a only",
+                        dev, prop.name, prop.major, prop.minor);
+        cudaMemPool_t pool;
+        VCB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t keep = UINT64_MAX;
+        VCB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        ready[dev] = true;
+    }
+    if (dev_out) *dev_out = dev;
+    return VCB_OK;
+}
+
+static int32_t use_device_of(int handle_dev) {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev != handle_dev) VCB_CUDA(cudaSetDevice(handle_dev));
+    return VCB_OK;
+}
+
+// Scratch that lives for one host call.
+struct Scratch {
+    std::vector<void*> ptrs;
+    cudaStream_t st;
+    explicit Scratch(cudaStream_t s) : st(s) {}
+    ~Scratch() { for (void* p : ptrs) cudaFreeAsync(p, st); }
+    template <class T>
+    cudaError_t get(T** out, size_t count) {
+        void* p = nullptr;
+        cudaError_t e = cudaMallocAsync(&p, std::max<size_t>(count, 1) * sizeof(T), st);
+        if (e == cudaSuccess) ptrs.push_back(p);
+        *out = static_cast<T*>(p);
+        return e;
+    }
+};
+
+static bool use_tc(const vcb_gmmmap& g, bool convert) {
+    const int v = g_variant.load();
+    if (v == 1) return false;
+    return tc_supported(g, convert);
+}
+
+static int32_t convert_device(const vcb_gmmmap& g, const double* dX, int64_t T, int64_t ldx,
+                              double* dY, int64_t ldy, bool copy_power, cudaStream_t st) {
+    if (use_tc(g, true)) return tc_convert(g, dX, T, ldx, dY, ldy, copy_power, st);
+    if (g_variant.load() == 2) return fail(VCB_EUNSUPPORTED, "tcgen05 kernel does not support this model shape (D=%d, M=%d)", g.D, g.M);
+    return simt_convert(g, dX, T, ldx, dY, ldy, copy_power, st);
+}
+
+static int32_t argmax_device(const vcb_gmmmap& g, const double* dX, int64_t T, int64_t ldx,
+                             int32_t* d_mhat, cudaStream_t st) {
+    if (use_tc(g, false)) return tc_argmax(g, dX, T, ldx, d_mhat, st);
+    if (g_variant.load() == 2) return fail(VCB_EUNSUPPORTED, "tcgen05 kernel does not support this model shape (D=%d, M=%d)", g.D, g.M);
+    return simt_argmax(g, dX, T, ldx, d_mhat, st);
+}
+
+// Chunk list of vc(c::TrajectoryConverter, fm) (src/common.jl:42-57) for a ragged batch.
+static void build_chunks(const int64_t* offsets, int64_t nseq, int chunk_limit, std::vector<int64_t>& chunks) {
+    chunks.clear();
+    chunks.push_back(offsets[0]);
+    for (int64_t s = 0; s < nseq; ++s) {
+        const int64_t b = offsets[s], e = offsets[s + 1];
+        if (chunk_limit <= 0) {
+            if (e > b) chunks.push_back(e);
+        } else {
+            for (int64_t c = b + chunk_limit; c < e; c += chunk_limit) chunks.push_back(c);
+            if (e > b) chunks.push_back(e);
+        }
+    }
+}
+
+static int32_t traj_device(const vcb_traj& t, const double* dX, int64_t ldx, const int64_t* offsets,
+                           int64_t nseq, int chunk_limit, double* dY, int64_t ldy, int64_t* dmhat,
+                           double* dEy, bool copy_power, cudaStream_t st) {
+    const vcb_gmmmap& g = *t.g;
+    if (nseq <= 0) return VCB_OK;
+    const int64_t base = offsets[0], total = offsets[nseq] - base;
+    for (int64_t s = 0; s < nseq; ++s)
+        if (offsets[s + 1] < offsets[s]) return fail(VCB_EARG, "offsets must be non-decreasing");
+    if (total == 0) return VCB_OK;
+    std::vector<int64_t> chunks;
+    build_chunks(offsets, nseq, chunk_limit, chunks);
+    for (auto& c : chunks) c -= base;
+    const int64_t nchunks = (int64_t)chunks.size() - 1;
+    int maxlen = 0;
+    for (int64_t c = 0; c < nchunks; ++c) maxlen = (int)std::max<int64_t>(maxlen, chunks[c + 1] - chunks[c]);
+    Scratch sc(st);
+    int32_t* d_mhat = nullptr;
+    int64_t* d_chunks = nullptr;
+    VCB_CUDA(sc.get(&d_mhat, (size_t)total));
+    VCB_CUDA(sc.get(&d_chunks, chunks.size()));
+    VCB_CUDA(cudaMemcpyAsync(d_chunks, chunks.data(), chunks.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    const double* X0 = dX + base * ldx;
+    VCB_TRY(argmax_device(g, X0, total, ldx, d_mhat, st));                       // src/trajectory_gmmmap.jl:82
+    VCB_TRY(traj_solve_device(t, X0, ldx, d_mhat, d_chunks, nchunks, maxlen, total, dY + base * ldy, ldy,
+                              dEy ? dEy + base * g.D : nullptr, copy_power, st));
+    if (dmhat) VCB_TRY(widen_mhat(d_mhat, total, dmhat + base, st));
+    return VCB_OK;
+}
+
+}  // namespace vcb
+
+using namespace vcb;
+
+#define VCB_GUARD_BEGIN try {
+#define VCB_GUARD_END                                                        \
+    }                                                                        \
+    catch (const std::bad_alloc&) { return fail(VCB_ENOMEM, "out of host memory"); } \
+    catch (...) { return fail(VCB_EARG, "unexpected internal error"); }
+
+extern "C" {
+
+int32_t vcb_version(void) { return VCB_VERSION; }
+
+int32_t vcb_last_error(char* buf, size_t buflen) {
+    if (!buf || buflen == 0) return VCB_EARG;
+    std::strncpy(buf, t_last_error.c_str(), buflen - 1);
+    buf[buflen - 1] = '\0';
+    return VCB_OK;
+}
+
+int32_t vcb_device_count(int32_t* count) {
+    if (!count) return fail(VCB_EARG, "null count");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *count = 0; return fail(VCB_ECUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    *count = n;
+    return VCB_OK;
+}
+
+int32_t vcb_set_device(int32_t device) {
+    VCB_CUDA(cudaSetDevice(device));
+    return ensure_device();
+}
+
+int32_t vcb_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return fail(VCB_EARG, "null ptr");
+    VCB_CUDA(cudaMallocHost(ptr, bytes));
+    return VCB_OK;
+}
+int32_t vcb_host_free(void* ptr) { VCB_CUDA(cudaFreeHost(ptr)); return VCB_OK; }
+int32_t vcb_host_register(void* ptr, size_t bytes) { VCB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault)); return VCB_OK; }
+int32_t vcb_host_unregister(void* ptr) { VCB_CUDA(cudaHostUnregister(ptr)); return VCB_OK; }
+
+int32_t vcb_set_kernel_variant(int32_t variant) {
+    if (variant < 0 || variant > 2) return fail(VCB_EARG, "variant must be 0, 1 or 2");
+    g_variant.store(variant);
+    return VCB_OK;
+}
+int64_t vcb_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------------
+// GMMMap
+// ------------------------------------------------------------------------------------------------
+int32_t vcb_gmmmap_create(const double* weights, const double* mu, const double* sigma, int32_t twoD,
+                          int32_t M, int32_t swap, vcb_gmmmap** out) {
+    VCB_GUARD_BEGIN
+    if (!out) return fail(VCB_EARG, "null out");
+    *out = nullptr;
+    int dev = 0;
+    VCB_TRY(ensure_device(&dev));
+    vcb_gmmmap* g = new vcb_gmmmap();
+    g->device = dev;
+    int32_t rc = build_gmmmap(weights, mu, sigma, twoD, M, swap, *g);
+    if (rc != VCB_OK) { delete g; return rc; }
+    *out = g;
+    return VCB_OK;
+    VCB_GUARD_END
+}
+
+int32_t vcb_gmmmap_destroy(vcb_gmmmap* g) {
+    if (!g) return VCB_OK;
+    use_device_of(g->device);
+    delete g;
+    return VCB_OK;
+}
+
+int32_t vcb_gmmmap_dim(const vcb_gmmmap* g, int32_t* dim) {
+    if (!g || !dim) return fail(VCB_EARG, "null argument");
+    *dim = g->D;
+    return VCB_OK;
+}
+int32_t vcb_gmmmap_ncomponents(const vcb_gmmmap* g, int32_t* M) {
+    if (!g || !M) return fail(VCB_EARG, "null argument");
+    *M = g->M;
+    return VCB_OK;
+}
+
+int32_t vcb_gmmmap_get_param(const vcb_gmmmap* g, int32_t which, double* out) {
+    if (!g || !out) return fail(VCB_EARG, "null argument");
+    const std::vector<double>* src = nullptr;
+    std::vector<double> tmp;
+    const int D = g->D, M = g->M;
+    switch (which) {
+        case 0: case 1: {  // stored [M][D] == column-major (D, M)
+            src = which == 0 ? &g->mux : &g->muy;
+            break;
+        }
+        case 2: src = &g->A; break;
+        case 3: src = &g->Sxx; break;
+        case 4: src = &g->Sxy; break;
+        case 5: src = &g->Syx; break;
+        case 6: src = &g->Syy; break;
+        case 7: src = &g->w; break;
+        default: return fail(VCB_EARG, "unknown parameter id %d", which);
+    }
+    (void)D; (void)M;
+    std::memcpy(out, src->data(), src->size() * sizeof(double));
+    return VCB_OK;
+}
+
+int32_t vcb_gmmmap_convert_dev(const vcb_gmmmap* g, const double* dX, int32_t xrows, int64_t T,
+                               int64_t ldx, double* dY, int64_t ldy, void* stream) {
+    VCB_GUARD_BEGIN
+    if (!g || (T > 0 && (!dX || !dY))) return fail(VCB_EARG, "null argument");
+    if (xrows != g->D) return fail(VCB_EDIM, "Inconsistent dimentions. (frame has %d rows, dim(g) = %d)", xrows, g->D);
+    if (T < 0 || ldx < xrows || ldy < xrows) return fail(VCB_EARG, "bad T/ld (T=%lld ldx=%lld ldy=%lld)", (long long)T, (long long)ldx, (long long)ldy);
+    VCB_TRY(use_device_of(g->device));
+    return convert_device(*g, dX, T, ldx, dY, ldy, false, (cudaStream_t)stream);
+    VCB_GUARD_END
+}
+
+int32_t vcb_gmmmap_vc_dev(const vcb_gmmmap* g, const double* dfm, int32_t rows, int64_t T, double* dout,
+                          void* stream) {
+    VCB_GUARD_BEGIN
+    if (!g || (T > 0 && (!dfm || !dout))) return fail(VCB_EARG, "null argument");
+    if (rows != g->D + 1) return fail(VCB_EDIM, "Inconsistent dimentions. (feature matrix has %d rows, expected 1 + dim(g) = %d)", rows, g->D + 1);
+    if (T < 0) return fail(VCB_EARG, "negative T");
+    VCB_TRY(use_device_of(g->device));
+    return convert_device(*g, dfm + 1, T, rows, dout + 1, rows, true, (cudaStream_t)stream);
+    VCB_GUARD_END
+}
+
+// Host pipeline shared by convert / vc: frames are cut into slices that rotate through NSLOT
+// (stream, device-in, device-out) slots so H2D, kernel and D2H of neighbouring slices overlap.
+static int32_t fbf_host(const vcb_gmmmap& g, const double* X, int64_t T, int64_t ldx, double* Y,
+                        int64_t ldy, bool whole_rows) {
+    if (T == 0) return VCB_OK;
+    constexpr int NSLOT = 3;
+    const int64_t slice = std::min<int64_t>(T, 131072);
+    // whole_rows (vc): X/Y point at row 1 of (rows, T) matrices with ld == rows; the copies move
+    // complete columns starting one double earlier (the power row).
+    const int64_t pre = whole_rows ? 1 : 0;
+    cudaStream_t st[NSLOT];
+    double *din[NSLOT], *dout[NSLOT];
+    int32_t rc = VCB_OK;
+    int made = 0;
+    for (int s = 0; s < NSLOT; ++s) { st[s] = nullptr; din[s] = dout[s] = nullptr; }
+    for (int s = 0; s < NSLOT && rc == VCB_OK; ++s) {
+        if (cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaMallocAsync((void**)&din[s], (size_t)slice * ldx * sizeof(double), st[s]) != cudaSuccess ||
+            cudaMallocAsync((void**)&dout[s], (size_t)slice * ldy * sizeof(double), st[s]) != cudaSuccess)
+            rc = fail(VCB_ECUDA, "staging allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        ++made;
+    }
+    int idx = 0;
+    for (int64_t b = 0; b < T && rc == VCB_OK; b += slice, idx = (idx + 1) % NSLOT) {
+        const int64_t n = std::min(slice, T - b);
+        const size_t in_elems = (size_t)(n - 1) * ldx + g.D + pre;
+        const size_t out_elems = (size_t)(n - 1) * ldy + g.D + pre;
+        cudaStream_t s = st[idx];
+        if (cudaMemcpyAsync(din[idx], X + b * ldx - pre, in_elems * sizeof(double), cudaMemcpyHostToDevice, s) != cudaSuccess) {
+            rc = fail(VCB_ECUDA, "H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        rc = convert_device(g, din[idx] + pre, n, ldx, dout[idx] + pre, ldy, whole_rows, s);
+        if (rc != VCB_OK) break;
+        if (whole_rows || ldy == g.D) {
+            if (cudaMemcpyAsync(Y + b * ldy - pre, dout[idx], out_elems * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess)
+                rc = fail(VCB_ECUDA, "D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        } else {
+            // strided output: only the D converted rows of each column belong to the caller
+            if (cudaMemcpy2DAsync(Y + b * ldy, ldy * sizeof(double), dout[idx], ldy * sizeof(double),
+                                  g.D * sizeof(double), n, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+                rc = fail(VCB_ECUDA, "D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+    }
+    for (int s = 0; s < made; ++s) {
+        if (st[s]) {
+            if (cudaStreamSynchronize(st[s]) != cudaSuccess && rc == VCB_OK)
+                rc = fail(VCB_ECUDA, "conversion failed: %s", cudaGetErrorString(cudaGetLastError()));
+            if (din[s]) cudaFreeAsync(din[s], st[s]);
+            if (dout[s]) cudaFreeAsync(dout[s], st[s]);
+            cudaStreamDestroy(st[s]);
+        }
+    }
+    return rc;
+}
+
+int32_t vcb_gmmmap_convert(const vcb_gmmmap* g, const double* X, int32_t xrows, int64_t T, int64_t ldx,
+                           double* Y, int64_t ldy) {
+    VCB_GUARD_BEGIN
+    if (!g || (T > 0 && (!X || !Y))) return fail(VCB_EARG, "null argument");
+    if (xrows != g->D) return fail(VCB_EDIM, "Inconsistent dimentions. (frame has %d rows, dim(g) = %d)", xrows, g->D);
+    if (T < 0 || ldx < xrows || ldy < xrows) return fail(VCB_EARG, "bad T/ld");
+    VCB_TRY(use_device_of(g->device));
+    return fbf_host(*g, X, T, ldx, Y, ldy, false);
+    VCB_GUARD_END
+}
+
+int32_t vcb_gmmmap_vc(const vcb_gmmmap* g, const double* fm, int32_t rows, int64_t T, double* out) {
+    VCB_GUARD_BEGIN
+    if (!g || (T > 0 && (!fm || !out))) return fail(VCB_EARG, "null argument");
+    if (rows != g->D + 1) return fail(VCB_EDIM, "Inconsistent dimentions. (feature matrix has %d rows, expected 1 + dim(g) = %d)", rows, g->D + 1);
+    if (T < 0) return fail(VCB_EARG, "negative T");
+    VCB_TRY(use_device_of(g->device));
+    return fbf_host(*g, fm + 1, T, rows, out + 1, rows, true);
+    VCB_GUARD_END
+}
+
+int32_t vcb_gmmmap_predict_proba(const vcb_gmmmap* g, const double* X, int32_t xrows, int64_t T,
+                                 int64_t ldx, double* post) {
+    VCB_GUARD_BEGIN
+    if (!g || (T > 0 && (!X || !post))) return fail(VCB_EARG, "null argument");
+    if (xrows != g->D) return fail(VCB_EDIM, "Inconsistent dimentions. (frame has %d rows, dim(g) = %d)", xrows, g->D);
+    if (T < 0 || ldx < xrows) return fail(VCB_EARG, "bad T/ld");
+    if (T == 0) return VCB_OK;
+    VCB_TRY(use_device_of(g->device));
+    cudaStream_t st = nullptr;
+    Scratch sc(st);
+    double *dX = nullptr, *dP = nullptr;
+    const size_t in_elems = (size_t)(T - 1) * ldx + xrows;
+    VCB_CUDA(sc.get(&dX, in_elems));
+    VCB_CUDA(sc.get(&dP, (size_t)T * g->M));
+    VCB_CUDA(cudaMemcpyAsync(dX, X, in_elems * sizeof(double), cudaMemcpyHostToDevice, st));
+    VCB_TRY(proba_fp64(*g, dX, T, ldx, dP, st));
+    VCB_CUDA(cudaMemcpyAsync(post, dP, (size_t)T * g->M * sizeof(double), cudaMemcpyDeviceToHost, st));
+    VCB_CUDA(cudaStreamSynchronize(st));
+    return VCB_OK;
+    VCB_GUARD_END
+}
+
+int32_t vcb_gmmmap_predict(const vcb_gmmmap* g, const double* X, int32_t xrows, int64_t T, int64_t ldx,
+                           int64_t* mhat) {
+    VCB_GUARD_BEGIN
+    if (!g || (T > 0 && (!X || !mhat))) return fail(VCB_EARG, "null argument");
+    if (xrows != g->D) return fail(VCB_EDIM, "Inconsistent dimentions. (frame has %d rows, dim(g) = %d)", xrows, g->D);
+    if (T < 0 || ldx < xrows) return fail(VCB_EARG, "bad T/ld");
+    if (T == 0) return VCB_OK;
+    VCB_TRY(use_device_of(g->device));
+    cudaStream_t st = nullptr;
+    Scratch sc(st);
+    double* dX = nullptr;
+    int32_t* dm = nullptr;
+    int64_t* dm64 = nullptr;
+    const size_t in_elems = (size_t)(T - 1) * ldx + xrows;
+    VCB_CUDA(sc.get(&dX, in_elems));
+    VCB_CUDA(sc.get(&dm, (size_t)T));
+    VCB_CUDA(sc.get(&dm64, (size_t)T));
+    VCB_CUDA(cudaMemcpyAsync(dX, X, in_elems * sizeof(double), cudaMemcpyHostToDevice, st));
+    VCB_TRY(argmax_device(*g, dX, T, ldx, dm, st));
+    VCB_TRY(widen_mhat(dm, T, dm64, st));
+    VCB_CUDA(cudaMemcpyAsync(mhat, dm64, (size_t)T * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    VCB_CUDA(cudaStreamSynchronize(st));
+    return VCB_OK;
+    VCB_GUARD_END
+}
+
+// ------------------------------------------------------------------------------------------------
+// TrajectoryGMMMap
+// ------------------------------------------------------------------------------------------------
+int32_t vcb_traj_create(const vcb_gmmmap* g, vcb_traj** out) {
+    VCB_GUARD_BEGIN
+    if (!g || !out) return fail(VCB_EARG, "null argument");
+    *out = nullptr;
+    VCB_TRY(use_device_of(g->device));
+    vcb_traj* t = new vcb_traj();
+    int32_t rc = build_traj(*g, *t);
+    if (rc != VCB_OK) { delete t; return rc; }
+    *out = t;
+    return VCB_OK;
+    VCB_GUARD_END
+}
+
+int32_t vcb_traj_destroy(vcb_traj* t) {
+    if (!t) return VCB_OK;
+    use_device_of(t->g->device);
+    delete t;
+    return VCB_OK;
+}
+
+int32_t vcb_traj_get_Dy(const vcb_traj* t, double* out) {
+    if (!t || !out) return fail(VCB_EARG, "null argument");
+    std::memcpy(out, t->Dy.data(), t->Dy.size() * sizeof(double));
+    return VCB_OK;
+}
+
+static int32_t traj_check(const vcb_traj* t, int32_t xrows, int64_t ldx, const int64_t* offsets, int64_t nseq) {
+    if (!t || !offsets) return fail(VCB_EARG, "null argument");
+    if (nseq < 0) return fail(VCB_EARG, "negative nseq");
+    // src/trajectory_gmmmap.jl:66-68
+    if (xrows != t->g->D) return fail(VCB_EDIM, "Inconsistent dimentions. (frame has %d rows, dim(t) = %d)", xrows, t->g->D);
+    if (ldx < xrows) return fail(VCB_EARG, "ldx < rows");
+    return VCB_OK;
+}
+
+int32_t vcb_traj_convert_batch_dev(const vcb_traj* t, const double* dX, int32_t xrows, int64_t ldx,
+                                   const int64_t* offsets, int64_t nseq, int32_t chunk_limit, double* dY,
+                                   int64_t ldy, int64_t* dmhat, double* dEy, void* stream) {
+    VCB_GUARD_BEGIN
+    VCB_TRY(traj_check(t, xrows, ldx, offsets, nseq));
+    if (!dX || !dY) return fail(VCB_EARG, "null argument");
+    if (ldy < t->Ds) return fail(VCB_EARG, "ldy < dim/2");
+    VCB_TRY(use_device_of(t->g->device));
+    return traj_device(*t, dX, ldx, offsets, nseq, chunk_limit, dY, ldy, dmhat, dEy, false, (cudaStream_t)stream);
+    VCB_GUARD_END
+}
+
+int32_t vcb_traj_vc_batch_dev(const vcb_traj* t, const double* dfm, int32_t rows, const int64_t* offsets,
+                              int64_t nseq, int32_t chunk_limit, double* dout, void* stream) {
+    VCB_GUARD_BEGIN
+    VCB_TRY(traj_check(t, rows - 1, rows, offsets, nseq));
+    if (!dfm || !dout) return fail(VCB_EARG, "null argument");
+    VCB_TRY(use_device_of(t->g->device));
+    return traj_device(*t, dfm + 1, rows, offsets, nseq, chunk_limit, dout + 1, t->Ds + 1, nullptr, nullptr, true,
+                       (cudaStream_t)stream);
+    VCB_GUARD_END
+}
+
+static int32_t traj_host(const vcb_traj& t, const double* X, int64_t ldx, const int64_t* offsets, int64_t nseq,
+                         int chunk_limit, double* Y, int64_t ldy, int64_t* mhat, double* Ey, bool whole_rows) {
+    if (nseq == 0) return VCB_OK;
+    const int64_t base = offsets[0], total = offsets[nseq] - base;
+    if (total <= 0) return VCB_OK;
+    const int D2 = t.g->D, Ds = t.Ds;
+    const int64_t pre = whole_rows ? 1 : 0;
+    cudaStream_t st = nullptr;
+    Scratch sc(st);
+    double *dX = nullptr, *dY = nullptr, *dE = nullptr;
+    int64_t* dm = nullptr;
+    const size_t in_elems = (size_t)(total - 1) * ldx + D2 + pre;
+    const size_t out_elems = (size_t)(total - 1) * ldy + Ds + pre;
+    VCB_CUDA(sc.get(&dX, in_elems));
+    VCB_CUDA(sc.get(&dY, out_elems));
+    if (mhat) VCB_CUDA(sc.get(&dm, (size_t)total));
+    if (Ey) VCB_CUDA(sc.get(&dE, (size_t)total * D2));
+    VCB_CUDA(cudaMemcpyAsync(dX, X + base * ldx - pre, in_elems * sizeof(double), cudaMemcpyHostToDevice, st));
+    std::vector<int64_t> rel(offsets, offsets + nseq + 1);
+    for (auto& o : rel) o -= base;
+    VCB_TRY(traj_device(t, dX + pre, ldx, rel.data(), nseq, chunk_limit, dY + pre, ldy, dm, dE, whole_rows, st));
+    if (whole_rows || ldy == Ds) {
+        VCB_CUDA(cudaMemcpyAsync(Y + base * ldy - pre, dY, out_elems * sizeof(double), cudaMemcpyDeviceToHost, st));
+    } else {
+        VCB_CUDA(cudaMemcpy2DAsync(Y + base * ldy, ldy * sizeof(double), dY, ldy * sizeof(double), Ds * sizeof(double),
+                                   total, cudaMemcpyDeviceToHost, st));
+    }
+    if (mhat) VCB_CUDA(cudaMemcpyAsync(mhat + base, dm, (size_t)total * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    if (Ey) VCB_CUDA(cudaMemcpyAsync(Ey + base * D2, dE, (size_t)total * D2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    VCB_CUDA(cudaStreamSynchronize(st));
+    return VCB_OK;
+}
+
+int32_t vcb_traj_convert_batch(const vcb_traj* t, const double* X, int32_t xrows, int64_t ldx,
+                               const int64_t* offsets, int64_t nseq, int32_t chunk_limit, double* Y,
+                               int64_t ldy, int64_t* mhat, double* Ey) {
+    VCB_GUARD_BEGIN
+    VCB_TRY(traj_check(t, xrows, ldx, offsets, nseq));
+    if (!X || !Y) return fail(VCB_EARG, "null argument");
+    if (ldy < t->Ds) return fail(VCB_EARG, "ldy < dim/2");
+    VCB_TRY(use_device_of(t->g->device));
+    return traj_host(*t, X, ldx, offsets, nseq, chunk_limit, Y, ldy, mhat, Ey, false);
+    VCB_GUARD_END
+}
+
+int32_t vcb_traj_vc_batch(const vcb_traj* t, const double* fm, int32_t rows, const int64_t* offsets,
+                          int64_t nseq, int32_t chunk_limit, double* out) {
+    VCB_GUARD_BEGIN
+    VCB_TRY(traj_check(t, rows - 1, rows, offsets, nseq));
+    if (!fm || !out) return fail(VCB_EARG, "null argument");
+    VCB_TRY(use_device_of(t->g->device));
+    return traj_host(*t, fm + 1, rows, offsets, nseq, chunk_limit, out + 1, t->Ds + 1, nullptr, nullptr, true);
+    VCB_GUARD_END
+}
+
+// ------------------------------------------------------------------------------------------------
+// DTW
+// ------------------------------------------------------------------------------------------------
+static int32_t dtw_check(const int64_t* toff, const int64_t* soff, int64_t npairs, int D) {
+    if (npairs < 0 || D < 1) return fail(VCB_EARG, "bad DTW batch (npairs=%lld, D=%d)", (long long)npairs, D);
+    if (npairs > 0 && (!toff || !soff)) return fail(VCB_EARG, "null offsets");
+    return VCB_OK;
+}
+
+int32_t vcb_dtw_fit_batch_dev(const double* dtmpl, const int64_t* tmpl_off, const double* dseq,
+                              const int64_t* seq_off, int64_t npairs, int32_t D, int32_t fstep,
+                              int32_t bstep, int64_t* dpaths, double* dfinal_cost, void* stream) {
+    VCB_GUARD_BEGIN
+    VCB_TRY(dtw_check(tmpl_off, seq_off, npairs, D));
+    if (npairs == 0) return VCB_OK;
+    if (!dtmpl || !dseq || !dpaths) return fail(VCB_EARG, "null argument");
+    VCB_TRY(ensure_device());
+    return dtw_fit_batch_device(dtmpl, tmpl_off, dseq, seq_off, npairs, D, fstep, bstep, dpaths, dfinal_cost,
+                                (cudaStream_t)stream);
+    VCB_GUARD_END
+}
+
+int32_t vcb_dtw_fit_batch(const double* tmpl, const int64_t* tmpl_off, const double* seq,
+                          const int64_t* seq_off, int64_t npairs, int32_t D, int32_t fstep, int32_t bstep,
+                          int64_t* paths, double* final_cost) {
+    VCB_GUARD_BEGIN
+    VCB_TRY(dtw_check(tmpl_off, seq_off, npairs, D));
+    if (npairs == 0) return VCB_OK;
+    if (!tmpl || !seq || !paths) return fail(VCB_EARG, "null argument");
+    VCB_TRY(ensure_device());
+    const int64_t tb = tmpl_off[0], sb = seq_off[0];
+    const int64_t nS = tmpl_off[npairs] - tb, nT = seq_off[npairs] - sb;
+    cudaStream_t st = nullptr;
+    Scratch sc(st);
+    double *dT = nullptr, *dS = nullptr, *dC = nullptr;
+    int64_t* dP = nullptr;
+    VCB_CUDA(sc.get(&dT, (size_t)nS * D));
+    VCB_CUDA(sc.get(&dS, (size_t)nT * D));
+    VCB_CUDA(sc.get(&dP, (size_t)nT));
+    VCB_CUDA(sc.get(&dC, (size_t)npairs));
+    VCB_CUDA(cudaMemcpyAsync(dT, tmpl + tb * D, (size_t)nS * D * sizeof(double), cudaMemcpyHostToDevice, st));
+    VCB_CUDA(cudaMemcpyAsync(dS, seq + sb * D, (size_t)nT * D * sizeof(double), cudaMemcpyHostToDevice, st));
+    std::vector<int64_t> to(tmpl_off, tmpl_off + npairs + 1), so(seq_off, seq_off + npairs + 1);
+    for (auto& o : to) o -= tb;
+    for (auto& o : so) o -= sb;
+    VCB_TRY(dtw_fit_batch_device(dT, to.data(), dS, so.data(), npairs, D, fstep, bstep, dP, dC, st));
+    VCB_CUDA(cudaMemcpyAsync(paths + sb, dP, (size_t)nT * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    if (final_cost) VCB_CUDA(cudaMemcpyAsync(final_cost, dC, (size_t)npairs * sizeof(double), cudaMemcpyDeviceToHost, st));
+    VCB_CUDA(cudaStreamSynchronize(st));
+    return VCB_OK;
+    VCB_GUARD_END
+}
+
+int32_t vcb_dtw_update(const double* tmpl, int32_t D, int32_t S, const double* lastcost, const double* v,
+                       int32_t fstep, int32_t bstep, double* newcost, int64_t* newbp) {
+    VCB_GUARD_BEGIN
+    if (!tmpl || !lastcost || !v || !newcost || !newbp) return fail(VCB_EARG, "null argument");
+    if (D < 1 || S < 1 || fstep < 0 || bstep < 0) return fail(VCB_EARG, "bad DTW arguments");
+    VCB_TRY(ensure_device());
+    cudaStream_t st = nullptr;
+    Scratch sc(st);
+    double *dT = nullptr, *dL = nullptr, *dV = nullptr, *dN = nullptr;
+    int64_t* dB = nullptr;
+    VCB_CUDA(sc.get(&dT, (size_t)S * D));
+    VCB_CUDA(sc.get(&dL, (size_t)S));
+    VCB_CUDA(sc.get(&dV, (size_t)D));
+    VCB_CUDA(sc.get(&dN, (size_t)S));
+    VCB_CUDA(sc.get(&dB, (size_t)S));
+    VCB_CUDA(cudaMemcpyAsync(dT, tmpl, (size_t)S * D * sizeof(double), cudaMemcpyHostToDevice, st));
+    VCB_CUDA(cudaMemcpyAsync(dL, lastcost, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, st));
+    VCB_CUDA(cudaMemcpyAsync(dV, v, (size_t)D * sizeof(double), cudaMemcpyHostToDevice, st));
+    VCB_TRY(dtw_update_device(dT, D, S, dL, dV, fstep, bstep, dN, dB, st));
+    VCB_CUDA(cudaMemcpyAsync(newcost, dN, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, st));
+    VCB_CUDA(cudaMemcpyAsync(newbp, dB, (size_t)S * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    VCB_CUDA(cudaStreamSynchronize(st));
+    return VCB_OK;
+    VCB_GUARD_END
+}
+
+// ------------------------------------------------------------------------------------------------
+// Callers either side of the path
+// ------------------------------------------------------------------------------------------------
+int32_t vcb_push_delta_batch(const double* src, int32_t D, const int64_t* offsets, int64_t nseq, double* out) {
+    VCB_GUARD_BEGIN
+    if (!src || !offsets || !out) return fail(VCB_EARG, "null argument");
+    if (D < 1 || nseq < 0) return fail(VCB_EARG, "bad arguments");
+    if (nseq == 0) return VCB_OK;
+    VCB_TRY(ensure_device());
+    const int64_t base = offsets[0], total = offsets[nseq] - base;
+    if (total <= 0) return VCB_OK;
+    cudaStream_t st = nullptr;
+    Scratch sc(st);
+    double *dI = nullptr, *dO = nullptr;
+    int64_t* dOff = nullptr;
+    VCB_CUDA(sc.get(&dI, (size_t)total * D));
+    VCB_CUDA(sc.get(&dO, (size_t)total * 2 * D));
+    VCB_CUDA(sc.get(&dOff, (size_t)nseq + 1));
+    std::vector<int64_t> rel(offsets, offsets + nseq + 1);
+    for (auto& o : rel) o -= base;
+    VCB_CUDA(cudaMemcpyAsync(dI, src + base * D, (size_t)total * D * sizeof(double), cudaMemcpyHostToDevice, st));
+    VCB_CUDA(cudaMemcpyAsync(dOff, rel.data(), rel.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    VCB_TRY(push_delta_device(dI, D, dOff, nseq, total, dO, st));
+    VCB_CUDA(cudaMemcpyAsync(out + base * 2 * D, dO, (size_t)total * 2 * D * sizeof(double), cudaMemcpyDeviceToHost, st));
+    VCB_CUDA(cudaStreamSynchronize(st));
+    return VCB_OK;
+    VCB_GUARD_END
+}
+
+int32_t vcb_align_batch(const double* src, const int64_t* src_off, const double* tgt, const int64_t* tgt_off,
+                        int64_t npairs, int32_t D, double* newtgt, int64_t* paths) {
+    VCB_GUARD_BEGIN
+    VCB_TRY(dtw_check(src_off, tgt_off, npairs, D));
+    if (npairs == 0) return VCB_OK;
+    if (!src || !tgt || !newtgt) return fail(VCB_EARG, "null argument");
+    VCB_TRY(ensure_device());
+    const int64_t sb = src_off[0], tb = tgt_off[0];
+    const int64_t nS = src_off[npairs] - sb, nT = tgt_off[npairs] - tb;
+    cudaStream_t st = nullptr;
+    Scratch sc(st);
+    double *dS = nullptr, *dT = nullptr, *dN = nullptr;
+    int64_t *dP = nullptr, *dOff = nullptr;
+    VCB_CUDA(sc.get(&dS, (size_t)nS * D));
+    VCB_CUDA(sc.get(&dT, (size_t)nT * D));
+    VCB_CUDA(sc.get(&dN, (size_t)nS * D));
+    VCB_CUDA(sc.get(&dP, (size_t)nT));
+    VCB_CUDA(sc.get(&dOff, 2 * ((size_t)npairs + 1)));
+    std::vector<int64_t> so(src_off, src_off + npairs + 1), to(tgt_off, tgt_off + npairs + 1);
+    for (auto& o : so) o -= sb;
+    for (auto& o : to) o -= tb;
+    VCB_CUDA(cudaMemcpyAsync(dS, src + sb * D, (size_t)nS * D * sizeof(double), cudaMemcpyHostToDevice, st));
+    VCB_CUDA(cudaMemcpyAsync(dT, tgt + tb * D, (size_t)nT * D * sizeof(double), cudaMemcpyHostToDevice, st));
+    VCB_CUDA(cudaMemcpyAsync(dOff, so.data(), so.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    VCB_CUDA(cudaMemcpyAsync(dOff + npairs + 1, to.data(), to.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    // align: template = source, sequence = target, DTW(fstep=0, bstep=2)  (src/align.jl:16-17)
+    VCB_TRY(dtw_fit_batch_device(dS, so.data(), dT, to.data(), npairs, D, 0, 2, dP, nullptr, st));
+    VCB_TRY(align_post_device(dT, dOff, dOff + npairs + 1, dP, npairs, D, dN, st));
+    VCB_CUDA(cudaMemcpyAsync(newtgt + sb * D, dN, (size_t)nS * D * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (paths) VCB_CUDA(cudaMemcpyAsync(paths + tb, dP, (size_t)nT * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    VCB_CUDA(cudaStreamSynchronize(st));
+    return VCB_OK;
+    VCB_GUARD_END
+}
+
+}  // extern "C"

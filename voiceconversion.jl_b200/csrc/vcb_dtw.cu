@@ -1,0 +1,304 @@
+// vcb_dtw.cu -- K4: batched DTW, bit-exact with DTWs.fit! + backward (reference src/dtw.jl:93-145).
+//
+// The reference recurrence is column-recursive: column t+1 of the cost table depends only on
+// column t (src/dtw.jl:113-121), so all template states of a column are independent.  One CTA
+// aligns one (template, sequence) pair with one thread per template state:
+//
+//   * observation costs (src/dtw.jl:33-35, sum_k (v_k - tmpl_k)^2 in strict left-to-right Float64
+//     without FMA contraction) are computed for a tile of TT sequence frames at once -- this is
+//     the FP64-pipe bound part and has TT independent dependency chains per thread;
+//   * the TT column updates then run back to back on a double-buffered shared-memory cost column
+//     (one __syncthreads per column); candidates are visited in the reference order
+//     i, i-bstep, ..., i+fstep with a strict `<`, sums associate as ((cost + ocost) + transition);
+//   * back-pointers are stored as (j - i + bstep) in BITS bits, packed 32/BITS columns per word in
+//     an L2-resident scratch (0.25 B/cell for the usual windows); the local-cost matrix and the
+//     cost table never exist in memory;
+//   * warp 0 back-tracks from the first minimum of the last column (src/dtw.jl:137), fetching
+//     back-pointer words 32 states at a time.
+//
+// The template is read through a k-major ("transposed") copy so the per-k loads are coalesced.
+#include <cstdlib>
+
+#include "vcb_kernels.h"
+
+namespace vcb {
+
+// tmpl (D, S) column-major per pair  ->  tmplT[k * S + i]
+__global__ void dtw_transpose_kernel(const double* __restrict__ tmpl, const int64_t* __restrict__ toff,
+                                     double* __restrict__ tmplT, int D) {
+    const int p = blockIdx.x;
+    const int64_t b = toff[p];
+    const int S = (int)(toff[p + 1] - b);
+    __shared__ double tile[32][33];
+    const int i0 = blockIdx.y * 32;
+    if (i0 >= S) return;
+    for (int k0 = 0; k0 < D; k0 += 32) {
+        // read: consecutive threads walk k (contiguous in the source)
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+            int i = i0 + r, k = k0 + threadIdx.x;
+            if (i < S && k < D) tile[r][threadIdx.x] = tmpl[(b + i) * D + k];
+        }
+        __syncthreads();
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+            int k = k0 + r, i = i0 + threadIdx.x;
+            if (i < S && k < D) tmplT[b * D + (int64_t)k * S + i] = tile[threadIdx.x][r];
+        }
+        __syncthreads();
+    }
+}
+
+template <int BITS, int TT, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+dtw_fused_kernel(const double* __restrict__ tmplT, const int64_t* __restrict__ toff,
+                 const double* __restrict__ seq, const int64_t* __restrict__ soff,
+                 const int64_t* __restrict__ bpoff, uint32_t* __restrict__ bp, int D, int fstep,
+                 int bstep, int64_t* __restrict__ paths, double* __restrict__ final_cost) {
+    constexpr int PER = 32 / BITS;
+    constexpr uint32_t MASK = (BITS == 32) ? 0xFFFFFFFFu : ((1u << BITS) - 1u);
+    const int p = blockIdx.x;
+    const int64_t tb = toff[p], sb = soff[p];
+    const int S = (int)(toff[p + 1] - tb);
+    const int T = (int)(soff[p + 1] - sb);
+    const int i = threadIdx.x;
+    const bool active = i < S;
+    const int Spad = (S + 31) & ~31;
+    uint32_t* bpp = bp + bpoff[p];  // [ceil(T/PER)][Spad]
+
+    extern __shared__ double smem[];
+    double* col0 = smem;                 // [Spad]
+    double* col1 = smem + Spad;          // [Spad]
+    double* vt = smem + 2 * Spad;        // [D][TT]  sequence tile, k-major
+    __shared__ double red_v[32];
+    __shared__ int red_i[32];
+    __shared__ int s_best;
+
+    const double* tcol = tmplT + tb * D + i;  // element k at tcol[k * S]
+    if (i < Spad) col0[i] = (double)(i + 1);   // src/dtw.jl:49  costtable[:,1] = 1:S
+    double* cur = col0;
+    double* nxt = col1;
+    uint32_t word = 0;
+
+    for (int t0 = 0; t0 < T; t0 += TT) {
+        const int ncols = min(TT, T - t0);
+        __syncthreads();  // previous tile's readers of vt are done; col init visible
+        for (int e = threadIdx.x; e < TT * D; e += blockDim.x) {
+            int c = e / D, k = e - c * D;
+            vt[k * TT + c] = (c < ncols) ? seq[(sb + t0 + c) * D + k] : 0.0;
+        }
+        __syncthreads();
+
+        // ---- observation costs for TT frames: acc[c] = sum_k (v[c][k] - tmpl[k])^2, in order
+        double acc[TT];
+#pragma unroll
+        for (int c = 0; c < TT; ++c) acc[c] = 0.0;
+        if (active) {
+            for (int k = 0; k < D; ++k) {
+                const double tk = tcol[(int64_t)k * S];
+                const double2* v2 = reinterpret_cast<const double2*>(vt + k * TT);
+#pragma unroll
+                for (int c = 0; c < TT; c += 2) {
+                    const double2 v = v2[c >> 1];
+                    const double d0 = __dsub_rn(v.x, tk), d1 = __dsub_rn(v.y, tk);
+                    acc[c] = __dadd_rn(acc[c], __dmul_rn(d0, d0));
+                    acc[c + 1] = __dadd_rn(acc[c + 1], __dmul_rn(d1, d1));
+                }
+            }
+        }
+
+        // ---- column recurrence  (src/dtw.jl:104-125)
+#pragma unroll
+        for (int c = 0; c < TT; ++c) {
+            if (c < ncols) {
+                if (active) {
+                    const double oc = acc[c];
+                    int minidx = i;
+                    double minc = __dadd_rn(__dadd_rn(cur[i], oc), 1.0);  // transition(i,i) = 1.0
+                    const int jlo = max(i - bstep, 0), jhi = min(i + fstep, S - 1);
+                    for (int j = jlo; j <= jhi; ++j) {
+                        double cand = __dadd_rn(cur[j], oc);
+                        // transition(j, i): 0.0 if i == j+1 (adding +0.0 to a non-negative sum is
+                        // the identity), 1.0 if i == j, 2.0 otherwise  (src/dtw.jl:23-31)
+                        if (i != j + 1) cand = __dadd_rn(cand, (i == j) ? 1.0 : 2.0);
+                        if (cand < minc) { minc = cand; minidx = j; }
+                    }
+                    nxt[i] = minc;
+                    word |= (uint32_t)(minidx - i + bstep) << (BITS * ((t0 + c) % PER));
+                }
+                const int t = t0 + c;
+                if ((t % PER) == PER - 1 || t == T - 1) {
+                    if (i < Spad) bpp[(int64_t)(t / PER) * Spad + i] = word;
+                    word = 0;
+                }
+                __syncthreads();
+                double* tmp = cur; cur = nxt; nxt = tmp;
+            }
+        }
+    }
+
+    // ---- indmin(costtable[:, T+1]) -- first minimum  (src/dtw.jl:137)
+    {
+        double v = active ? cur[i] : __longlong_as_double(0x7FF0000000000000LL);
+        int idx = active ? i : 0x7FFFFFFF;
+        // NaN never wins a `<` in the reference's scan unless it is first; keep it simple: treat
+        // NaN as +inf except at index 0 (cannot occur for finite inputs).
+        if (v != v && i != 0) v = __longlong_as_double(0x7FF0000000000000LL);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ov = __shfl_down_sync(0xFFFFFFFFu, v, o);
+            int oi = __shfl_down_sync(0xFFFFFFFFu, idx, o);
+            if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+        }
+        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+        if (l == 0) { red_v[w] = v; red_i[w] = idx; }
+        __syncthreads();
+        if (w == 0) {
+            const int nw = (blockDim.x + 31) >> 5;
+            v = (l < nw) ? red_v[l] : __longlong_as_double(0x7FF0000000000000LL);
+            idx = (l < nw) ? red_i[l] : 0x7FFFFFFF;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                double ov = __shfl_down_sync(0xFFFFFFFFu, v, o);
+                int oi = __shfl_down_sync(0xFFFFFFFFu, idx, o);
+                if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+            }
+            if (l == 0) {
+                s_best = idx;
+                if (final_cost) final_cost[p] = v;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- backward  (src/dtw.jl:139-142); back-pointer stores above are visible after the barrier
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int st = s_best;
+        int64_t* path = paths + sb;
+        if (lane == 0) path[T - 1] = st + 1;
+        int cur_wi = -1, wbase = 0;
+        uint32_t w = 0;
+        for (int t = T - 1; t >= 1; --t) {
+            const int wi = t / PER;
+            if (wi != cur_wi || st < wbase || st >= wbase + 32) {
+                wbase = (fstep == 0) ? st - 31 : st - 16;
+                wbase = max(0, min(wbase, Spad - 32));
+                w = bpp[(int64_t)wi * Spad + wbase + lane];
+                cur_wi = wi;
+            }
+            const uint32_t ww = __shfl_sync(0xFFFFFFFFu, w, st - wbase);
+            const int code = (int)((ww >> (BITS * (t % PER))) & MASK);
+            st = st + code - bstep;
+            if (lane == 0) path[t - 1] = st + 1;
+        }
+    }
+}
+
+template <int BITS>
+static int32_t launch_dtw(const double* tmplT, const int64_t* d_toff, const double* seq,
+                          const int64_t* d_soff, const int64_t* d_bpoff, uint32_t* bp, int D,
+                          int fstep, int bstep, int64_t npairs, int maxS, int64_t* paths,
+                          double* final_cost, cudaStream_t st) {
+    constexpr int TT = 16;
+    const int nt = round_up(maxS, 32);
+    const size_t smem = (size_t)(2 * nt + D * TT) * sizeof(double);
+    // VCB_DTW_MINB=2 selects the 2-CTA/SM build (48 registers, spills the cost tile) for tuning.
+    static const int minb = [] { const char* e = getenv("VCB_DTW_MINB"); return e ? atoi(e) : 1; }();
+    if (nt <= 640) {
+        auto k = minb >= 2 ? dtw_fused_kernel<BITS, TT, 640, 2> : dtw_fused_kernel<BITS, TT, 640, 1>;
+        VCB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<(unsigned)npairs, nt, smem, st>>>(tmplT, d_toff, seq, d_soff, d_bpoff, bp, D, fstep, bstep, paths, final_cost);
+    } else {
+        auto k = dtw_fused_kernel<BITS, TT, 1024, 1>;
+        VCB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<(unsigned)npairs, nt, smem, st>>>(tmplT, d_toff, seq, d_soff, d_bpoff, bp, D, fstep, bstep, paths, final_cost);
+    }
+    count_launch();
+    VCB_CUDA(cudaGetLastError());
+    return VCB_OK;
+}
+
+int32_t dtw_fit_batch_device(const double* d_tmpl, const int64_t* h_toff, const double* d_seq,
+                             const int64_t* h_soff, int64_t npairs, int D, int fstep, int bstep,
+                             int64_t* d_paths, double* d_final_cost, cudaStream_t st) {
+    if (npairs == 0) return VCB_OK;
+    if (D < 1 || fstep < 0 || bstep < 0) return fail(VCB_EARG, "bad DTW arguments (D=%d fstep=%d bstep=%d)", D, fstep, bstep);
+    const int window = fstep + bstep + 1;
+    if (window > 256) return fail(VCB_EUNSUPPORTED, "DTW window fstep+bstep+1 = %d > 256", window);
+    const int bits = window <= 4 ? 2 : (window <= 16 ? 4 : 8);
+    const int per = 32 / bits;
+    int maxS = 0;
+    std::vector<int64_t> bpoff(npairs + 1, 0);
+    for (int64_t p = 0; p < npairs; ++p) {
+        const int64_t S = h_toff[p + 1] - h_toff[p], T = h_soff[p + 1] - h_soff[p];
+        if (S < 1 || T < 1) return fail(VCB_EARG, "pair %lld has an empty template or sequence", (long long)p);
+        if (S > 1024) return fail(VCB_EUNSUPPORTED, "template of %lld frames: this build aligns templates of up to 1024 frames", (long long)S);
+        maxS = (int)std::max<int64_t>(maxS, S);
+        bpoff[p + 1] = bpoff[p] + ((T + per - 1) / per) * ((S + 31) / 32 * 32);
+    }
+    const int64_t totalS = h_toff[npairs];
+    // scratch: offsets, transposed templates, packed back-pointers (stream-ordered allocation)
+    int64_t* d_off = nullptr;
+    double* d_tmplT = nullptr;
+    uint32_t* d_bp = nullptr;
+    const size_t noff = (size_t)(npairs + 1);
+    VCB_CUDA(cudaMallocAsync((void**)&d_off, 3 * noff * sizeof(int64_t), st));
+    VCB_CUDA(cudaMallocAsync((void**)&d_tmplT, (size_t)totalS * D * sizeof(double), st));
+    VCB_CUDA(cudaMallocAsync((void**)&d_bp, (size_t)std::max<int64_t>(bpoff[npairs], 1) * sizeof(uint32_t), st));
+    // offsets are tiny; pageable async copies complete before return of the call for the host
+    // buffers involved (they are staged by the driver), bpoff lives until we synchronise below.
+    VCB_CUDA(cudaMemcpyAsync(d_off, h_toff, noff * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    VCB_CUDA(cudaMemcpyAsync(d_off + noff, h_soff, noff * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    VCB_CUDA(cudaMemcpyAsync(d_off + 2 * noff, bpoff.data(), noff * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    {
+        dim3 grid((unsigned)npairs, (maxS + 31) / 32), block(32, 8);
+        dtw_transpose_kernel<<<grid, block, 0, st>>>(d_tmpl, d_off, d_tmplT, D);
+        count_launch();
+        VCB_CUDA(cudaGetLastError());
+    }
+    int32_t rc;
+    if (bits == 2)
+        rc = launch_dtw<2>(d_tmplT, d_off, d_seq, d_off + noff, d_off + 2 * noff, d_bp, D, fstep, bstep, npairs, maxS, d_paths, d_final_cost, st);
+    else if (bits == 4)
+        rc = launch_dtw<4>(d_tmplT, d_off, d_seq, d_off + noff, d_off + 2 * noff, d_bp, D, fstep, bstep, npairs, maxS, d_paths, d_final_cost, st);
+    else
+        rc = launch_dtw<8>(d_tmplT, d_off, d_seq, d_off + noff, d_off + 2 * noff, d_bp, D, fstep, bstep, npairs, maxS, d_paths, d_final_cost, st);
+    cudaFreeAsync(d_off, st);
+    cudaFreeAsync(d_tmplT, st);
+    cudaFreeAsync(d_bp, st);
+    return rc;
+}
+
+// One column of the recurrence: update!(d, v)  (src/dtw.jl:61-90)
+__global__ void dtw_update_kernel(const double* __restrict__ tmpl, int D, int S,
+                                  const double* __restrict__ last, const double* __restrict__ v,
+                                  int fstep, int bstep, double* __restrict__ newcost,
+                                  int64_t* __restrict__ newbp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    double oc = 0.0;
+    for (int k = 0; k < D; ++k) {
+        const double d = __dsub_rn(v[k], tmpl[(int64_t)i * D + k]);
+        oc = __dadd_rn(oc, __dmul_rn(d, d));
+    }
+    int minidx = i;
+    double minc = __dadd_rn(__dadd_rn(last[i], oc), 1.0);
+    const int jlo = max(i - bstep, 0), jhi = min(i + fstep, S - 1);
+    for (int j = jlo; j <= jhi; ++j) {
+        double cand = __dadd_rn(last[j], oc);
+        if (i != j + 1) cand = __dadd_rn(cand, (i == j) ? 1.0 : 2.0);
+        if (cand < minc) { minc = cand; minidx = j; }
+    }
+    newcost[i] = minc;
+    newbp[i] = minidx + 1;
+}
+
+int32_t dtw_update_device(const double* d_tmpl, int D, int S, const double* d_last,
+                          const double* d_v, int fstep, int bstep, double* d_newcost,
+                          int64_t* d_newbp, cudaStream_t st) {
+    dtw_update_kernel<<<(S + 127) / 128, 128, 0, st>>>(d_tmpl, D, S, d_last, d_v, fstep, bstep, d_newcost, d_newbp);
+    count_launch();
+    VCB_CUDA(cudaGetLastError());
+    return VCB_OK;
+}
+
+}  // namespace vcb

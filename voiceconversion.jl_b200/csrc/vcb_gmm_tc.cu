@@ -1,0 +1,487 @@
+// vcb_gmm_tc.cu -- K1/K2 on the 5th-generation tensor cores (tcgen05 + TMEM), 3xTF32.
+//
+// Same mathematics as vcb_gmm_simt.cu (reference src/gmmmap.jl:101-118, src/gmm.jl:24-58), laid
+// out as one GEMM per 128-frame tile:
+//
+//     [128 frames x KP]  .  [KP x N]      KP = [xc (D) | 1 | 0-pad],  N = G mixtures x rows
+//        A = [xc | 1]          B = per mixture the rows of Linv_m (whitening, offset folded into
+//                                  the "1" column) and, for conversion, of [A_m | b_m]
+//
+// so that TMEM receives z_m = Linv_m (x - mux_m) and Ey_m = muy_m + A_m (x - mux_m) for G mixtures
+// per MMA chunk.  fp32 accuracy is needed (real models have cond(Sxx) ~ 1e7; plain TF32 misses the
+// 1e-4 parity bar by three orders of magnitude), so both operands are split into tf32 hi + lo
+// and each k-step issues three MMAs (hi.hi, hi.lo, lo.hi) into the same fp32 accumulator.
+//
+// Warp roles (one persistent CTA per SM, 320 threads):
+//   warps 0-3  epilogue: tcgen05.ld their 32 TMEM lanes (one frame per thread), |z|^2 -> log-lik,
+//              online soft-max, posterior-weighted accumulation of Ey (conversion) or running
+//              top-2 (arg-max).  Per-mixture means and log-likelihoods never leave the SM.
+//   warp 4     B producer: cp.async.bulk (TMA 1-D) of pre-packed operand images, ring of stages.
+//   warp 5     MMA issuer: one lane issues tcgen05.mma / tcgen05.commit; owns the TMEM allocation.
+//   warps 6-9  A loaders: read Float64 frames, centre in Float64, split to tf32 hi/lo, write the
+//              UMMA K-major (no-swizzle) image to shared memory, double-buffered across tiles.
+// Pipelines: smem B ring (full/empty), A double buffer (full/empty), TMEM accumulator double
+// buffer (full/empty) -- all mbarriers; tcgen05.commit signals the "empty"/"full" transitions.
+#include "vcb_kernels.h"
+
+namespace vcb {
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kThreads = 320;
+constexpr int kMaxStages = 4;
+
+struct TcParams {
+    const double* X; int64_t T; int64_t ldx;
+    const double* xbar;
+    const float* B;        // [NCH][2][N*KP] operand images (hi, lo)
+    const float* cst;      // [NCH*G]
+    int D, KP, G, NCH, N, stages, abufs;
+    int64_t ntiles;
+    double* Y; int64_t ldy; int copy_power;
+    int32_t* mhat; int* flag_count; int64_t* flag_list;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem], kind::tf32, single CTA
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// mbarrier arrives once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+                 : "r"(taddr));
+    v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+    v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float to_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+// K-major, non-swizzled operand: 8-row x 16-byte core matrices; LBO = byte distance between
+// consecutive 16-byte K slices, SBO = byte distance between consecutive 8-row groups.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+    return d;                // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
+}
+
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4)                      // D format: F32
+           | (2u << 7) | (2u << 10)       // A, B format: TF32
+           | (0u << 15) | (0u << 16)      // A, B K-major
+           | ((uint32_t)(N >> 3) << 17)   // N / 8
+           | ((uint32_t)(M >> 4) << 24);  // M / 16
+}
+
+// ---------------------------------------------------------------------------------------------
+// The kernel
+// ---------------------------------------------------------------------------------------------
+template <int DP, bool CONVERT>
+__global__ void __launch_bounds__(kThreads, 1)
+gmm_tc_kernel(const TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KP = p.KP, N = p.N, NCH = p.NCH, S = p.stages, AB = p.abufs;
+    constexpr int ROWS = CONVERT ? 2 * DP : DP;  // TMEM columns per mixture
+
+    // ---- shared memory carve-up
+    const uint32_t a_half = kTileM * KP * 4;      // one of hi / lo
+    const uint32_t a_bytes = 2 * a_half;
+    const uint32_t b_half = (uint32_t)N * KP * 4;
+    const uint32_t b_bytes = 2 * b_half;
+    uint8_t* a_smem = smem_raw;
+    uint8_t* b_smem = a_smem + (size_t)AB * a_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + (size_t)S * b_bytes);
+    // bars: a_full[2], a_empty[2], acc_full[2], acc_empty[2], b_full[kMaxStages], b_empty[kMaxStages]
+    const uint32_t bar0 = smem_u32(bars);
+    auto a_full = [&](int i) { return bar0 + 8u * i; };
+    auto a_empty = [&](int i) { return bar0 + 8u * (2 + i); };
+    auto acc_full = [&](int i) { return bar0 + 8u * (4 + i); };
+    auto acc_empty = [&](int i) { return bar0 + 8u * (6 + i); };
+    auto b_full = [&](int i) { return bar0 + 8u * (8 + i); };
+    auto b_empty = [&](int i) { return bar0 + 8u * (8 + kMaxStages + i); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * kMaxStages);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(a_full(i), 128);
+            mbar_init(a_empty(i), 1);
+            mbar_init(acc_full(i), 1);
+            mbar_init(acc_empty(i), 128);
+        }
+        for (int i = 0; i < kMaxStages; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
+        fence_barrier_init();
+    }
+    if (warp == 5) tmem_alloc(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int64_t my_tiles = (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+
+    if (warp == 4) {
+        // ======================= B producer =======================
+        if (lane == 0) {
+            const int64_t total = my_tiles * NCH;
+            for (int64_t it = 0; it < total; ++it) {
+                const int s = (int)(it % S);
+                const uint32_t ph = (uint32_t)((it / S) & 1);
+                const int c = (int)(it % NCH);
+                mbar_wait(b_empty(s), ph ^ 1);
+                mbar_expect_tx(b_full(s), b_bytes);
+                bulk_g2s(smem_u32(b_smem + (size_t)s * b_bytes), p.B + (size_t)c * 2 * N * KP, b_bytes, b_full(s));
+            }
+        }
+    } else if (warp == 5) {
+        // ======================= MMA issuer =======================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(kTileM, N);
+            const int ksteps = KP / 8;
+            int64_t it = 0;
+            for (int64_t tl = 0; tl < my_tiles; ++tl) {
+                const int ab = (int)(tl % AB);
+                const uint32_t aph = (uint32_t)((tl / AB) & 1);
+                mbar_wait(a_full(ab), aph);
+                const uint32_t a_hi = smem_u32(a_smem + (size_t)ab * a_bytes);
+                const uint32_t a_lo = a_hi + a_half;
+                for (int c = 0; c < NCH; ++c, ++it) {
+                    const int s = (int)(it % S);
+                    const uint32_t ph = (uint32_t)((it / S) & 1);
+                    const int acc = (int)(it & 1);
+                    const uint32_t accph = (uint32_t)((it >> 1) & 1);
+                    mbar_wait(b_full(s), ph);
+                    mbar_wait(acc_empty(acc), accph ^ 1);
+                    tc_fence_after();
+                    const uint32_t b_hi = smem_u32(b_smem + (size_t)s * b_bytes);
+                    const uint32_t b_lo = b_hi + b_half;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
+                    for (int kk = 0; kk < ksteps; ++kk) {
+                        // one k-step = 8 tf32 = two 16-byte K slices
+                        const uint32_t aoff = (uint32_t)kk * 2u * (kTileM * 16u);
+                        const uint32_t boff = (uint32_t)kk * 2u * ((uint32_t)N * 16u);
+                        const uint64_t dah = make_desc(a_hi + aoff, kTileM * 16u, 128u);
+                        const uint64_t dal = make_desc(a_lo + aoff, kTileM * 16u, 128u);
+                        const uint64_t dbh = make_desc(b_hi + boff, (uint32_t)N * 16u, 128u);
+                        const uint64_t dbl = make_desc(b_lo + boff, (uint32_t)N * 16u, 128u);
+                        umma_tf32(d_tmem, dal, dbh, idesc, kk > 0 ? 1u : 0u);  // small terms first
+                        umma_tf32(d_tmem, dah, dbl, idesc, 1u);
+                        umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+                    }
+                    umma_commit(b_empty(s));     // B stage may be refilled once these MMAs retire
+                    umma_commit(acc_full(acc));  // accumulator ready for the epilogue
+                    if (c == NCH - 1) umma_commit(a_empty(ab));
+                }
+            }
+        }
+    } else if (warp >= 6) {
+        // ======================= A loaders (128 threads, one frame row each) =======================
+        const int row = threadIdx.x - 6 * 32;
+        const uint32_t row_off = (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
+        for (int64_t tl = 0; tl < my_tiles; ++tl) {
+            const int ab = (int)(tl % AB);
+            const uint32_t aph = (uint32_t)((tl / AB) & 1);
+            const int64_t tile = blockIdx.x + tl * gridDim.x;
+            const int64_t t = tile * kTileM + row;
+            mbar_wait(a_empty(ab), aph ^ 1);
+            uint8_t* hi = a_smem + (size_t)ab * a_bytes;
+            uint8_t* lo = hi + a_half;
+            const bool live = t < p.T;
+            const double* x = p.X + (live ? t : 0) * p.ldx;
+            for (int k4 = 0; k4 < KP / 4; ++k4) {
+                float4 h, l;
+                float* hp = &h.x;
+                float* lp = &l.x;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = 4 * k4 + j;
+                    double v = 0.0;
+                    if (live && k < p.D) v = x[k] - p.xbar[k];
+                    else if (k == p.D) v = 1.0;
+                    const float fh = to_tf32((float)v);
+                    hp[j] = fh;
+                    lp[j] = to_tf32((float)(v - (double)fh));
+                }
+                const uint32_t off = (uint32_t)k4 * (kTileM * 16u) + row_off;
+                *reinterpret_cast<float4*>(hi + off) = h;
+                *reinterpret_cast<float4*>(lo + off) = l;
+            }
+            fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+            mbar_arrive(a_full(ab));
+        }
+    } else {
+        // ======================= epilogue (warps 0-3; thread = frame = TMEM lane) =======================
+        const int row = threadIdx.x;  // 0..127
+        const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+        int64_t it = 0;
+        for (int64_t tl = 0; tl < my_tiles; ++tl) {
+            const int64_t tile = blockIdx.x + tl * gridDim.x;
+            const int64_t t = tile * kTileM + row;
+            float mx = -INFINITY, sum = 0.f, second = -INFINITY, qbest = 0.f;
+            int best = 0;
+            float y[CONVERT ? DP : 1];
+            if (CONVERT) {
+#pragma unroll
+                for (int r = 0; r < DP; ++r) y[r] = 0.f;
+            }
+            for (int c = 0; c < NCH; ++c, ++it) {
+                const int acc = (int)(it & 1);
+                const uint32_t accph = (uint32_t)((it >> 1) & 1);
+                mbar_wait(acc_full(acc), accph);
+                tc_fence_after();
+                const uint32_t tcol = tmem_base + lane_base + (uint32_t)(acc * N);
+                for (int g = 0; g < p.G; ++g) {
+                    const int m = c * p.G + g;
+                    const uint32_t mcol = tcol + (uint32_t)(g * ROWS);
+                    // ---- |z|^2 over the DP whitening columns
+                    float q = 0.f;
+#pragma unroll
+                    for (int r0 = 0; r0 < DP; r0 += 32) {
+                        float v[32];
+#pragma unroll
+                        for (int r = 0; r < 32; r += 8)
+                            if (r0 + r < DP) tmem_ld8(mcol + r0 + r, v + r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int r = 0; r < 32; ++r)
+                            if (r0 + r < DP) q = fmaf(v[r], v[r], q);
+                    }
+                    const float l = fmaf(-0.5f, q, p.cst[m]);  // -inf for padding mixtures
+                    if (CONVERT) {
+                        if (l > mx) {
+                            const float a = __expf(mx - l);
+                            sum *= a;
+#pragma unroll
+                            for (int r = 0; r < DP; ++r) y[r] *= a;
+                            mx = l;
+                        }
+                        const float w = (l == -INFINITY) ? 0.f : __expf(l - mx);
+                        sum += w;
+#pragma unroll
+                        for (int r0 = 0; r0 < DP; r0 += 32) {
+                            float v[32];
+#pragma unroll
+                            for (int r = 0; r < 32; r += 8)
+                                if (r0 + r < DP) tmem_ld8(mcol + DP + r0 + r, v + r);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int r = 0; r < 32; ++r)
+                                if (r0 + r < DP) y[r0 + r] = fmaf(w, v[r], y[r0 + r]);
+                        }
+                    } else {
+                        if (l > mx) { second = mx; mx = l; best = m; qbest = q; }
+                        else if (l > second) second = l;
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(acc_empty(acc));
+            }
+            if (t < p.T) {
+                if (CONVERT) {
+                    const float inv = 1.0f / sum;
+                    double* yo = p.Y + t * p.ldy;
+#pragma unroll
+                    for (int r = 0; r < DP; ++r)
+                        if (r < p.D) yo[r] = (double)(y[r] * inv);
+                    if (p.copy_power) yo[-1] = p.X[t * p.ldx - 1];  // src/common.jl:23
+                } else {
+                    p.mhat[t] = best;
+                    if (mx - second < 1e-3f * (1.0f + qbest) || !(mx == mx)) {
+                        const int slot = atomicAdd(p.flag_count, 1);
+                        p.flag_list[slot] = t;
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+template <int DP, bool CONVERT>
+int32_t launch_tc(const TcParams& p, size_t smem, cudaStream_t st) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    auto k = gmm_tc_kernel<DP, CONVERT>;
+    VCB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)std::min<int64_t>(p.ntiles, sms);
+    k<<<grid, kThreads, smem, st>>>(p);
+    count_launch();
+    VCB_CUDA(cudaGetLastError());
+    return VCB_OK;
+}
+
+template <bool CONVERT>
+int32_t dispatch_tc(int DP, const TcParams& p, size_t smem, cudaStream_t st) {
+    switch (DP) {
+        case 8: return launch_tc<8, CONVERT>(p, smem, st);
+        case 16: return launch_tc<16, CONVERT>(p, smem, st);
+        case 24: return launch_tc<24, CONVERT>(p, smem, st);
+        case 32: return launch_tc<32, CONVERT>(p, smem, st);
+        case 40: return launch_tc<40, CONVERT>(p, smem, st);
+        case 48: return launch_tc<48, CONVERT>(p, smem, st);
+        case 56: return launch_tc<56, CONVERT>(p, smem, st);
+        case 64: return launch_tc<64, CONVERT>(p, smem, st);
+        default: break;
+    }
+    if (!CONVERT) {
+        switch (DP) {
+            case 72: return launch_tc<72, false>(p, smem, st);
+            case 80: return launch_tc<80, false>(p, smem, st);
+            case 88: return launch_tc<88, false>(p, smem, st);
+            case 96: return launch_tc<96, false>(p, smem, st);
+            default: break;
+        }
+    }
+    return fail(VCB_EUNSUPPORTED, "tcgen05 kernel: unsupported padded dimension %d", DP);
+}
+
+constexpr size_t kSmemLimit = 227 * 1024;
+constexpr size_t kBarBytes = 1024;
+
+}  // namespace
+
+TcPlan tc_plan(int M, int KP, int rows_per_mixture) {
+    TcPlan best;
+    const int dp = rows_per_mixture;  // caller passes DP or 2*DP
+    (void)dp;
+    const int gmax = 256 / rows_per_mixture;
+    if (gmax < 1) return best;
+    // candidate groupings ordered by (padded mixture count, larger G first)
+    for (int abufs = 2; abufs >= 1 && best.G == 0; --abufs) {
+        int best_pad = 1 << 30;
+        for (int g = gmax; g >= 1; --g) {
+            const int n = g * rows_per_mixture;
+            if (n % 16) continue;
+            const size_t a = (size_t)abufs * 2 * kTileM * KP * 4;
+            const size_t bst = (size_t)2 * n * KP * 4;
+            if (a + 2 * bst + kBarBytes > kSmemLimit) continue;
+            const int padded = (M + g - 1) / g * g;
+            if (padded < best_pad) {
+                best_pad = padded;
+                int stages = (int)((kSmemLimit - kBarBytes - a) / bst);
+                if (stages > kMaxStages) stages = kMaxStages;
+                best.G = g; best.N = n; best.stages = stages; best.abufs = abufs;
+                best.smem = a + (size_t)stages * bst + kBarBytes;
+            }
+        }
+    }
+    return best;
+}
+
+bool tc_supported(const vcb_gmmmap& g, bool convert) {
+    if (convert) return g.tc.GC > 0 && g.DP <= 64;
+    return g.tc.GW > 0 && g.DP <= 96;
+}
+
+static void fill_common(const vcb_gmmmap& g, const double* dX, int64_t T, int64_t ldx, bool convert, TcParams& p,
+                        size_t& smem) {
+    const TcPlan plan = tc_plan(g.M, g.tc.KP, convert ? 2 * g.DP : g.DP);
+    p.X = dX; p.T = T; p.ldx = ldx; p.xbar = g.d_xbar.p;
+    p.B = convert ? g.tc.Bc.p : g.tc.Bw.p;
+    p.cst = g.tc.cst.p;
+    p.D = g.D; p.KP = g.tc.KP; p.G = plan.G; p.N = plan.N;
+    p.NCH = convert ? g.tc.NCHC : g.tc.NCHW;
+    p.stages = plan.stages; p.abufs = plan.abufs;
+    p.ntiles = (T + kTileM - 1) / kTileM;
+    smem = plan.smem;
+}
+
+int32_t tc_convert(const vcb_gmmmap& g, const double* dX, int64_t T, int64_t ldx, double* dY, int64_t ldy,
+                   bool copy_power, cudaStream_t st) {
+    if (T == 0) return VCB_OK;
+    TcParams p{};
+    size_t smem = 0;
+    fill_common(g, dX, T, ldx, true, p, smem);
+    p.Y = dY; p.ldy = ldy; p.copy_power = copy_power ? 1 : 0;
+    return dispatch_tc<true>(g.DP, p, smem, st);
+}
+
+int32_t tc_argmax(const vcb_gmmmap& g, const double* dX, int64_t T, int64_t ldx, int32_t* d_mhat,
+                  cudaStream_t st) {
+    if (T == 0) return VCB_OK;
+    int* d_count = nullptr;
+    int64_t* d_list = nullptr;
+    VCB_CUDA(cudaMallocAsync((void**)&d_count, sizeof(int), st));
+    VCB_CUDA(cudaMallocAsync((void**)&d_list, (size_t)T * sizeof(int64_t), st));
+    VCB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), st));
+    TcParams p{};
+    size_t smem = 0;
+    fill_common(g, dX, T, ldx, false, p, smem);
+    p.mhat = d_mhat; p.flag_count = d_count; p.flag_list = d_list;
+    int32_t rc = dispatch_tc<false>(g.DP, p, smem, st);
+    if (rc == VCB_OK) rc = recheck_argmax_fp64(g, dX, ldx, d_count, d_list, d_mhat, st);
+    cudaFreeAsync(d_count, st);
+    cudaFreeAsync(d_list, st);
+    return rc;
+}
+
+}  // namespace vcb
