@@ -12,10 +12,14 @@
 //   R[t][t-2] = -1/4 Pdd_{t-1}
 // (terms that reach outside 0..T-1 vanish), and with g_t = P_t E_t = [u_t; v_t]:
 //   r_t = u_t + 1/2 v_{t-1} - 1/2 v_{t+1}.
-// One CTA factorises one chunk by block Cholesky, sequential in time and parallel inside the
-// Ds x Ds block operations, holding the three-block-row window in shared memory; per frame it
-// streams L[t][t]^-1, L[t][t-1], L[t][t-2] (3 Ds^2 doubles) to HBM once and reads them once in the
-// back substitution (cp.async double-buffered).
+// One CTA of 64 threads factorises one chunk by block Cholesky, sequential in time.  The threads
+// form an 8 x 8 grid of TS x TS register tiles (Ds <= 8*TS), so the Ds x Ds block products run
+// register-blocked out of column-major shared-memory operands (the FP64 pipe, not shared-memory
+// bandwidth, is the limiter), and the Cholesky of the diagonal block keeps its S and L^-1 tiles in
+// registers, broadcasting one column / row per elimination step.  The three-block-row window lives
+// in shared memory; per frame L[t][t]^-1, L[t][t-1], L[t][t-2] (3 Ds^2 doubles) are streamed to
+// HBM once and read once by the cp.async double-buffered back substitution.  Several CTAs share
+// an SM so one chunk's latency-bound Cholesky overlaps another chunk's products.
 #include <cstdlib>
 
 #include "vcb_kernels.h"
@@ -80,7 +84,7 @@ struct TrajParams {
     const int32_t* mhat;    // [total] 0-based
     const double* Gv;       // [total][D2]  g_t = P_t E_t
     const int64_t* chunk_off;
-    double* Lst;            // [total][3][Ds*Ds]  transposes of Linv_tt, L[t][t-1], L[t][t-2] (compact)
+    double* Lst;            // [total][3][Ds*Ds]  Linv_tt, L[t][t-1], L[t][t-2], row-major, compact
     double* Z;              // [total][Ds]
     double* Y; int64_t ldy;
     const double* Xpow; int64_t ldx; int copy_power;
@@ -88,193 +92,244 @@ struct TrajParams {
     int* err;
 };
 
-// Shared-memory block (row-major, leading dimension LD = Ds|1 to spread banks).
-#define BLK(b, i, j) (b)[(i) * LD + (j)]
+// C (TS x TS register tile at rows i0.., cols j0..) (+)= sign * X * Y'   for k in [0, kmax),
+// X and Y stored column-major in shared memory: XT[k*LD + i] = X[i][k].
+template <int TS, int LD, bool SUB>
+__device__ __forceinline__ void tile_xyt(double (&c)[TS][TS], const double* __restrict__ XT,
+                                         const double* __restrict__ YT, int i0, int j0, int kmax) {
+#pragma unroll 2
+    for (int k = 0; k < kmax; ++k) {
+        double a[TS], b[TS];
+#pragma unroll
+        for (int x = 0; x < TS; ++x) a[x] = XT[k * LD + i0 + x];
+#pragma unroll
+        for (int y = 0; y < TS; ++y) b[y] = YT[k * LD + j0 + y];
+#pragma unroll
+        for (int x = 0; x < TS; ++x)
+#pragma unroll
+            for (int y = 0; y < TS; ++y) c[x][y] = SUB ? fma(-a[x], b[y], c[x][y]) : fma(a[x], b[y], c[x][y]);
+    }
+}
 
-template <int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB)
-traj_solve_kernel(const TrajParams p) {
-    const int Ds = p.Ds, D2 = 2 * Ds, LD = Ds | 1, BB = Ds * Ds;
-    const int tid = threadIdx.x, NT = blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+// One CTA (64 threads = 8 x 8 grid of TS x TS register tiles) per chunk; Ds <= DSP = 8*TS, the
+// padding rows/columns carry a unit diagonal so the factorisation is unaffected.
+template <int TS>
+__global__ void __launch_bounds__(64, (TS <= 3) ? 5 : ((TS == 4) ? 3 : 1))
+traj_solve_tiled(const TrajParams p) {
+    constexpr int DSP = 8 * TS, LD = DSP + 1, BS = DSP * LD;
+    const int Ds = p.Ds, D2 = 2 * Ds, BB = Ds * Ds;
+    const int tid = threadIdx.x;
+    const int ti = tid & 7, tj = tid >> 3, i0 = ti * TS, j0 = tj * TS;
     const int64_t c0 = p.chunk_off[blockIdx.x];
     const int T = (int)(p.chunk_off[blockIdx.x + 1] - c0);
     if (T <= 0) return;
 
     extern __shared__ __align__(16) double sm[];
-    const int BS = Ds * LD;  // doubles per block buffer
-    double* Rtt = sm;
-    double* Rt1 = Rtt + BS;
-    double* Rt2 = Rt1 + BS;
-    double* G2 = Rt2 + BS;
-    double* Tm = G2 + BS;
-    double* S = Tm + BS;
-    double* gbuf[2] = {S + BS, S + 2 * BS};                    // G1 / L[t-1][t-2]
-    double* ibuf[3] = {S + 3 * BS, S + 4 * BS, S + 5 * BS};    // Linv_t, Linv_{t-1}, Linv_{t-2}
-    double* vec = S + 6 * BS;  // r[Ds], tmp[Ds], z0[Ds], z1[Ds], z2[Ds]
-    double* rv = vec;
-    double* tmpv = vec + Ds;
-    double* zb[3] = {vec + 2 * Ds, vec + 3 * Ds, vec + 4 * Ds};
+    double* Rt1 = sm;                 // R[t][t-1], overwritten in place by Tm
+    double* Rt2 = Rt1 + BS;           // R[t][t-2]
+    double* G2 = Rt2 + BS;            // L[t][t-2]
+    double* gbuf[2] = {G2 + BS, G2 + 2 * BS};                       // L[t][t-1] / L[t-1][t-2]
+    double* ibuf[3] = {G2 + 3 * BS, G2 + 4 * BS, G2 + 5 * BS};      // Linv_t, Linv_{t-1}, Linv_{t-2}
+    double* vec = G2 + 6 * BS;
+    double* colb[2] = {vec, vec + DSP};
+    double* wrowb[2] = {vec + 2 * DSP, vec + 3 * DSP};
+    double* rv = vec + 4 * DSP;
+    double* tmpv = vec + 5 * DSP;
+    double* zb[3] = {vec + 6 * DSP, vec + 7 * DSP, vec + 8 * DSP};
+    for (int e = tid; e < 8 * BS + 9 * DSP; e += 64) sm[e] = 0.0;
 
     const int32_t* mh = p.mhat + c0;
     const double* gv = p.Gv + c0 * D2;
     double* Lst = p.Lst + c0 * 3 * BB;
     double* Zg = p.Z + c0 * Ds;
+    __syncthreads();
 
     // =========================== forward: block Cholesky + L z = r ===========================
     for (int t = 0; t < T; ++t) {
         double* G1 = gbuf[t & 1];
-        double* Lt1t2 = gbuf[(t & 1) ^ 1];
+        const double* Lt1t2 = gbuf[(t & 1) ^ 1];
         double* W = ibuf[t % 3];
-        double* Lm1inv = ibuf[(t + 2) % 3];
-        double* Lm2inv = ibuf[(t + 1) % 3];
+        const double* Lm1inv = ibuf[(t + 2) % 3];
+        const double* Lm2inv = ibuf[(t + 1) % 3];
         double* zt = zb[t % 3];
         const double* z1 = zb[(t + 2) % 3];
         const double* z2 = zb[(t + 1) % 3];
+        const double* Pt = p.P + (size_t)mh[t] * D2 * D2;
+        const double* Pm = (t >= 1) ? p.P + (size_t)mh[t - 1] * D2 * D2 : nullptr;
+        const double* Pp = (t + 1 < T) ? p.P + (size_t)mh[t + 1] * D2 * D2 : nullptr;
 
-        // ---- 0. assemble R[t][t], R[t][t-1], R[t][t-2] and r_t
-        {
-            const double* Pt = p.P + (size_t)mh[t] * D2 * D2;
-            const double* Pm = (t >= 1) ? p.P + (size_t)mh[t - 1] * D2 * D2 : nullptr;
-            const double* Pp = (t + 1 < T) ? p.P + (size_t)mh[t + 1] * D2 * D2 : nullptr;
-            for (int e = tid; e < BB; e += NT) {
-                // e = j*Ds + i so that consecutive threads read consecutive rows of a column
-                const int j = e / Ds, i = e - j * Ds;
-                double rtt = Pt[i + (size_t)j * D2];
-                double rt1 = 0.0, rt2 = 0.0;
-                if (Pm) {
-                    const double pdd = Pm[(Ds + i) + (size_t)(Ds + j) * D2];
-                    rtt = fma(0.25, pdd, rtt);
-                    rt1 = 0.5 * Pm[(Ds + i) + (size_t)j * D2] - 0.5 * Pt[i + (size_t)(Ds + j) * D2];
-                    if (t >= 2) rt2 = -0.25 * pdd;
+        // ---- 0. own tile of R[t][t] straight into the S accumulators (loads overlap steps 1-3);
+        //         R[t][t-1], R[t][t-2] and r_t staged column-major in shared memory
+        double s[TS][TS];
+#pragma unroll
+        for (int x = 0; x < TS; ++x)
+#pragma unroll
+            for (int y = 0; y < TS; ++y) {
+                const int i = i0 + x, j = j0 + y;
+                double v = (i == j) ? 1.0 : 0.0;
+                if (i < Ds && j < Ds) {
+                    v = Pt[i + (size_t)j * D2];
+                    if (Pm) v = fma(0.25, Pm[(Ds + i) + (size_t)(Ds + j) * D2], v);
+                    if (Pp) v = fma(0.25, Pp[(Ds + i) + (size_t)(Ds + j) * D2], v);
                 }
-                if (Pp) rtt = fma(0.25, Pp[(Ds + i) + (size_t)(Ds + j) * D2], rtt);
-                BLK(Rtt, i, j) = rtt;
-                BLK(Rt1, i, j) = rt1;
-                BLK(Rt2, i, j) = rt2;
+                s[x][y] = v;
             }
+        for (int e = tid; e < BB; e += 64) {
+            const int j = e / Ds, i = e - j * Ds;
+            double rt1 = 0.0, rt2 = 0.0;
+            if (Pm) {
+                rt1 = 0.5 * Pm[(Ds + i) + (size_t)j * D2] - 0.5 * Pt[i + (size_t)(Ds + j) * D2];
+                if (t >= 2) rt2 = -0.25 * Pm[(Ds + i) + (size_t)(Ds + j) * D2];
+            }
+            Rt1[j * LD + i] = rt1;
+            Rt2[j * LD + i] = rt2;
+        }
+        if (tid < DSP) {
+            double r = 0.0;
             if (tid < Ds) {
-                double r = gv[(size_t)t * D2 + tid];
+                r = gv[(size_t)t * D2 + tid];
                 if (t >= 1) r = fma(0.5, gv[(size_t)(t - 1) * D2 + Ds + tid], r);
                 if (t + 1 < T) r = fma(-0.5, gv[(size_t)(t + 1) * D2 + Ds + tid], r);
-                rv[tid] = r;
             }
+            rv[tid] = r;
         }
         __syncthreads();
-        // ---- 1. G2 = L[t][t-2] = R[t][t-2] * Linv_{t-2}'   (Linv lower: k <= j)
-        for (int e = tid; e < BB; e += NT) {
-            const int i = e / Ds, j = e - i * Ds;
-            double s = 0.0;
-            if (t >= 2)
-                for (int k = 0; k <= j; ++k) s = fma(BLK(Rt2, i, k), BLK(Lm2inv, j, k), s);
-            BLK(G2, i, j) = s;
+        const int ktri = min(j0 + TS, DSP);  // Linv is lower triangular: Linv[j][k] = 0 for k > j
+        // ---- 1. G2 = L[t][t-2] = R[t][t-2] * Linv_{t-2}'
+        {
+            double c[TS][TS] = {};
+            if (t >= 2) tile_xyt<TS, LD, false>(c, Rt2, Lm2inv, i0, j0, ktri);
+#pragma unroll
+            for (int y = 0; y < TS; ++y)
+#pragma unroll
+                for (int x = 0; x < TS; ++x) G2[(j0 + y) * LD + i0 + x] = c[x][y];
         }
         __syncthreads();
-        // ---- 2. Tm = R[t][t-1] - G2 * L[t-1][t-2]'
-        for (int e = tid; e < BB; e += NT) {
-            const int i = e / Ds, j = e - i * Ds;
-            double s = BLK(Rt1, i, j);
-            if (t >= 2)
-                for (int k = 0; k < Ds; ++k) s = fma(-BLK(G2, i, k), BLK(Lt1t2, j, k), s);
-            BLK(Tm, i, j) = s;
+        // ---- 2. Tm = R[t][t-1] - G2 * L[t-1][t-2]'   (in place, every thread owns its tile)
+        if (t >= 2) {
+            double c[TS][TS];
+#pragma unroll
+            for (int y = 0; y < TS; ++y)
+#pragma unroll
+                for (int x = 0; x < TS; ++x) c[x][y] = Rt1[(j0 + y) * LD + i0 + x];
+            tile_xyt<TS, LD, true>(c, G2, Lt1t2, i0, j0, DSP);
+#pragma unroll
+            for (int y = 0; y < TS; ++y)
+#pragma unroll
+                for (int x = 0; x < TS; ++x) Rt1[(j0 + y) * LD + i0 + x] = c[x][y];
         }
         __syncthreads();
         // ---- 3. G1 = L[t][t-1] = Tm * Linv_{t-1}'
-        for (int e = tid; e < BB; e += NT) {
-            const int i = e / Ds, j = e - i * Ds;
-            double s = 0.0;
-            if (t >= 1)
-                for (int k = 0; k <= j; ++k) s = fma(BLK(Tm, i, k), BLK(Lm1inv, j, k), s);
-            BLK(G1, i, j) = s;
+        {
+            double c[TS][TS] = {};
+            if (t >= 1) tile_xyt<TS, LD, false>(c, Rt1, Lm1inv, i0, j0, ktri);
+#pragma unroll
+            for (int y = 0; y < TS; ++y)
+#pragma unroll
+                for (int x = 0; x < TS; ++x) G1[(j0 + y) * LD + i0 + x] = c[x][y];
         }
         __syncthreads();
-        // ---- 4. S = R[t][t] - G2 G2' - G1 G1'  (lower triangle), W = I
-        for (int e = tid; e < BB; e += NT) {
-            const int i = e / Ds, j = e - i * Ds;
-            if (j <= i) {
-                double s = BLK(Rtt, i, j);
-                if (t >= 1)
-                    for (int k = 0; k < Ds; ++k) s = fma(-BLK(G1, i, k), BLK(G1, j, k), s);
-                if (t >= 2)
-                    for (int k = 0; k < Ds; ++k) s = fma(-BLK(G2, i, k), BLK(G2, j, k), s);
-                BLK(S, i, j) = s;
-            } else {
-                BLK(S, i, j) = 0.0;
+        // ---- 4. S = R[t][t] - G2 G2' - G1 G1'
+        if (t >= 2) tile_xyt<TS, LD, true>(s, G2, G2, i0, j0, DSP);
+        if (t >= 1) tile_xyt<TS, LD, true>(s, G1, G1, i0, j0, DSP);
+        // ---- 5. right-looking Cholesky of S fused with W <- L^-1; S and W tiles stay in
+        //         registers, column k of S and row k of W are broadcast through shared memory
+        double w[TS][TS];
+#pragma unroll
+        for (int x = 0; x < TS; ++x)
+#pragma unroll
+            for (int y = 0; y < TS; ++y) w[x][y] = (i0 + x == j0 + y) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < DSP; ++k) {
+            constexpr int dummy = 0; (void)dummy;
+            const int kt = k / TS, kb = k % TS;
+            double* col = colb[k & 1];
+            double* wrow = wrowb[k & 1];
+            if (tj == kt) {
+#pragma unroll
+                for (int x = 0; x < TS; ++x) col[i0 + x] = s[x][kb];
             }
-            BLK(W, i, j) = (i == j) ? 1.0 : 0.0;
-        }
-        __syncthreads();
-        // ---- 5. right-looking Cholesky of S fused with W <- L^-1 (forward substitution on I).
-        //         The diagonal of L is never written back (only L^-1, G1, G2 are kept), so two
-        //         barriers per column suffice.
-        for (int k = 0; k < Ds; ++k) {
-            const double skk = BLK(S, k, k);
+            if (ti == kt) {
+#pragma unroll
+                for (int y = 0; y < TS; ++y) wrow[j0 + y] = w[kb][y];
+            }
+            __syncthreads();
+            const double skk = col[k];
             if (!(skk > 0.0) && tid == 0) atomicExch(p.err, 1);
-            const double dinv = 1.0 / sqrt(skk);
-            for (int e = tid; e < 2 * Ds; e += NT) {
-                if (e < Ds) {              // column k of L (below the diagonal)
-                    if (e > k) BLK(S, e, k) *= dinv;
-                } else {                   // row k of L^-1
-                    const int j = e - Ds;
-                    if (j <= k) BLK(W, k, j) *= dinv;
+            const double dinv = rsqrt(skk);
+            double li[TS], lj[TS], xj[TS];
+#pragma unroll
+            for (int x = 0; x < TS; ++x) li[x] = col[i0 + x] * dinv;
+#pragma unroll
+            for (int y = 0; y < TS; ++y) { lj[y] = col[j0 + y] * dinv; xj[y] = wrow[j0 + y] * dinv; }
+#pragma unroll
+            for (int x = 0; x < TS; ++x)
+#pragma unroll
+                for (int y = 0; y < TS; ++y) {
+                    const int i = i0 + x, j = j0 + y;
+                    if (i > k) {
+                        if (j > k) s[x][y] = fma(-li[x], lj[y], s[x][y]);
+                        else w[x][y] = fma(-li[x], xj[y], w[x][y]);
+                    } else if (i == k && j <= k) {
+                        w[x][y] = xj[y];
+                    }
                 }
-            }
-            __syncthreads();
-            for (int e = tid; e < BB; e += NT) {
-                const int i = e / Ds, j = e - i * Ds;
-                if (i > k) {
-                    const double lik = BLK(S, i, k);
-                    if (j > k && j <= i) BLK(S, i, j) = fma(-lik, BLK(S, j, k), BLK(S, i, j));
-                    else if (j <= k) BLK(W, i, j) = fma(-lik, BLK(W, k, j), BLK(W, i, j));
-                }
-            }
-            __syncthreads();
         }
-        // ---- 6. z_t = Linv (r - G1 z_{t-1} - G2 z_{t-2})
-        for (int j = warp; j < Ds; j += nwarps) {
-            double s = 0.0;
-            for (int k = lane; k < Ds; k += 32) {
-                if (t >= 1) s = fma(BLK(G1, j, k), z1[k], s);
-                if (t >= 2) s = fma(BLK(G2, j, k), z2[k], s);
+#pragma unroll
+        for (int y = 0; y < TS; ++y)
+#pragma unroll
+            for (int x = 0; x < TS; ++x) W[(j0 + y) * LD + i0 + x] = w[x][y];
+        __syncthreads();
+        // ---- 6. z_t = Linv (r - G1 z_{t-1} - G2 z_{t-2})   (thread = row)
+        if (tid < DSP) {
+            double s0 = 0.0, s1 = 0.0;
+            if (t >= 1) {
+#pragma unroll 4
+                for (int k = 0; k < DSP; ++k) s0 = fma(G1[k * LD + tid], z1[k], s0);
             }
-            s = warp_sum(s);
-            if (lane == 0) tmpv[j] = rv[j] - s;
+            if (t >= 2) {
+#pragma unroll 4
+                for (int k = 0; k < DSP; ++k) s1 = fma(G2[k * LD + tid], z2[k], s1);
+            }
+            tmpv[tid] = rv[tid] - (s0 + s1);
         }
         __syncthreads();
-        for (int i = warp; i < Ds; i += nwarps) {
-            double s = 0.0;
-            for (int j = lane; j <= i; j += 32) s = fma(BLK(W, i, j), tmpv[j], s);
-            s = warp_sum(s);
-            if (lane == 0) { zt[i] = s; Zg[(size_t)t * Ds + i] = s; }
+        if (tid < DSP) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll 2
+            for (int k = 0; k + 1 < DSP; k += 2) {
+                s0 = fma(W[k * LD + tid], tmpv[k], s0);
+                s1 = fma(W[(k + 1) * LD + tid], tmpv[k + 1], s1);
+            }
+            const double z = s0 + s1;
+            zt[tid] = z;
+            if (tid < Ds) Zg[(size_t)t * Ds + tid] = z;
         }
-        // ---- 7. stream the three blocks of block-row t to HBM, TRANSPOSED (the back
-        //         substitution multiplies by L', so it reads rows)
+        // ---- 7. stream the three blocks of block-row t to HBM (row-major, compact)
         {
             double* dst = Lst + (size_t)t * 3 * BB;
-            for (int e = tid; e < BB; e += NT) {
-                const int j = e / Ds, i = e - j * Ds;   // dst[j][i] = src[i][j]
-                dst[e] = BLK(W, i, j);
-                dst[BB + e] = BLK(G1, i, j);
-                dst[2 * BB + e] = BLK(G2, i, j);
+            for (int e = tid; e < BB; e += 64) {
+                const int i = e / Ds, j = e - i * Ds;
+                dst[e] = W[j * LD + i];
+                dst[BB + e] = G1[j * LD + i];
+                dst[2 * BB + e] = G2[j * LD + i];
             }
         }
         __syncthreads();
     }
 
     // =========================== backward: L' y = z ===========================================
-    // y_t = Linv_t' (z_t - L[t+1][t]' y_{t+1} - L[t+2][t]' y_{t+2})
-    // Needs Linv_t (slot 0 of row t), L[t+1][t] (slot 1 of row t+1), L[t+2][t] (slot 2 of row t+2).
-    double* bb[2][3] = {{Rtt, Rt1, Rt2}, {G2, Tm, S}};  // compact Ds*Ds images, double-buffered
+    // y_t = Linv_t' (z_t - L[t+1][t]' y_{t+1} - L[t+2][t]' y_{t+2});  thread = output row j
+    double* bb[2][3] = {{sm, sm + BB, sm + 2 * BB}, {sm + 3 * BB, sm + 4 * BB, sm + 5 * BB}};
     double* yb[3] = {zb[0], zb[1], zb[2]};
+    const bool vec_ok = (BB % 2) == 0;
     auto prefetch = [&](int t, int buf) {
         const int n16 = BB / 2;  // 16-byte pieces per block
-        for (int e = tid; e < 3 * n16; e += NT) {
+        for (int e = tid; e < 3 * n16; e += 64) {
             const int b = e / n16, o = e - b * n16;
-            const int row = t + b;
-            if (row < T) cp_async16(bb[buf][b] + 2 * o, Lst + ((size_t)row * 3 + b) * BB + 2 * o);
+            if (t + b < T) cp_async16(bb[buf][b] + 2 * o, Lst + ((size_t)(t + b) * 3 + b) * BB + 2 * o);
         }
     };
-    const bool vec_ok = (BB % 2) == 0;
     if (vec_ok) { prefetch(T - 1, (T - 1) & 1); cp_async_commit(); }
     for (int t = T - 1; t >= 0; --t) {
         const int buf = t & 1;
@@ -286,41 +341,48 @@ traj_solve_kernel(const TrajParams p) {
             cp_async_commit();
             cp_async_wait<1>();
         } else {
-            for (int e = tid; e < 3 * BB; e += NT) {
+            for (int e = tid; e < 3 * BB; e += 64) {
                 const int b = e / BB, o = e - b * BB;
                 if (t + b < T) bb[buf][b][o] = Lst[((size_t)(t + b) * 3 + b) * BB + o];
             }
         }
-        if (tid < Ds) tmpv[tid] = Zg[(size_t)t * Ds + tid];
         __syncthreads();
         const double* Li = bb[buf][0];
         const double* L1 = bb[buf][1];
         const double* L2 = bb[buf][2];
-        for (int j = warp; j < Ds; j += nwarps) {
-            double s = 0.0;
-            for (int i = lane; i < Ds; i += 32) {
-                if (t + 1 < T) s = fma(L1[j * Ds + i], y1[i], s);
-                if (t + 2 < T) s = fma(L2[j * Ds + i], y2[i], s);
-            }
-            s = warp_sum(s);
-            if (lane == 0) rv[j] = tmpv[j] - s;
+        if (tid < Ds) {
+            double s0 = 0.0, s1 = 0.0;
+            if (t + 1 < T)
+                for (int i = 0; i < Ds; ++i) s0 = fma(L1[i * Ds + tid], y1[i], s0);
+            if (t + 2 < T)
+                for (int i = 0; i < Ds; ++i) s1 = fma(L2[i * Ds + tid], y2[i], s1);
+            rv[tid] = Zg[(size_t)t * Ds + tid] - (s0 + s1);
         }
         __syncthreads();
-        for (int j = warp; j < Ds; j += nwarps) {
-            double s = 0.0;
-            for (int i = j + lane; i < Ds; i += 32) s = fma(Li[j * Ds + i], rv[i], s);
-            s = warp_sum(s);
-            if (lane == 0) {
-                yt[j] = s;
-                p.Y[(c0 + t) * p.ldy + j] = s;  // reshape(y, D, T)  src/trajectory_gmmmap.jl:109
-            }
+        if (tid < Ds) {
+            double s0 = 0.0;
+            for (int i = tid; i < Ds; ++i) s0 = fma(Li[i * Ds + tid], rv[i], s0);
+            yt[tid] = s0;
+            p.Y[(c0 + t) * p.ldy + tid] = s0;  // reshape(y, D, T)  src/trajectory_gmmmap.jl:109
         }
-        if (p.copy_power && tid == 0) p.Y[(c0 + t) * p.ldy - 1] = p.Xpow[(c0 + t) * p.ldx - 1];  // src/common.jl:60
+        if (p.copy_power && tid == 63) p.Y[(c0 + t) * p.ldy - 1] = p.Xpow[(c0 + t) * p.ldx - 1];  // src/common.jl:60
         __syncthreads();
     }
 }
 
 }  // namespace
+
+template <int TS>
+static int32_t launch_tiled(const TrajParams& p, int64_t nchunks, cudaStream_t st) {
+    constexpr int DSP = 8 * TS, LD = DSP + 1;
+    const size_t smem = ((size_t)8 * DSP * LD + 9 * DSP) * sizeof(double);
+    auto k = traj_solve_tiled<TS>;
+    VCB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)nchunks, 64, smem, st>>>(p);
+    count_launch();
+    VCB_CUDA(cudaGetLastError());
+    return VCB_OK;
+}
 
 int32_t traj_solve_device(const vcb_traj& tr, const double* dX, int64_t ldx, const int32_t* d_mhat,
                           const int64_t* d_chunk_off, int64_t nchunks, int max_chunk_len,
@@ -329,9 +391,8 @@ int32_t traj_solve_device(const vcb_traj& tr, const double* dX, int64_t ldx, con
     (void)max_chunk_len;
     if (total == 0 || nchunks == 0) return VCB_OK;
     const vcb_gmmmap& g = *tr.g;
-    const int Ds = tr.Ds, D2 = 2 * Ds, BB = Ds * Ds, LD = Ds | 1;
-    const size_t smem = ((size_t)12 * Ds * LD + 5 * Ds) * sizeof(double);
-    if (smem > 227 * 1024) return fail(VCB_EUNSUPPORTED, "static dimension %d too large for the trajectory solver (shared memory)", Ds);
+    const int Ds = tr.Ds, D2 = 2 * Ds, BB = Ds * Ds;
+    if (Ds > 48) return fail(VCB_EUNSUPPORTED, "static dimension %d exceeds the trajectory solver's limit (48)", Ds);
 
     double *dE = nullptr, *dG = nullptr, *dL = nullptr, *dZ = nullptr;
     int* derr = nullptr;
@@ -349,30 +410,27 @@ int32_t traj_solve_device(const vcb_traj& tr, const double* dX, int64_t ldx, con
         count_launch();
         VCB_CUDA(cudaGetLastError());
     }
+    int32_t rc;
     {
         TrajParams p{};
         p.P = tr.d_P.p; p.mhat = d_mhat; p.Gv = dG; p.chunk_off = d_chunk_off; p.Lst = dL; p.Z = dZ;
         p.Y = dY; p.ldy = ldy; p.Xpow = dX; p.ldx = ldx; p.copy_power = copy_power ? 1 : 0;
         p.Ds = Ds; p.err = derr;
-        int nt = round_up(BB, 32);
-        if (nt > 1024) nt = round_up((BB + 1) / 2, 32);
-        if (nt > 1024) nt = 1024;
-        // Resident CTAs per SM trade registers (spills) for latency hiding; VCB_TRAJ_MINB=1|2|3
-        // overrides the default for tuning runs.
-        static const int minb = [] { const char* e = getenv("VCB_TRAJ_MINB"); return e ? atoi(e) : 3; }();
-        void (*k)(const TrajParams) = traj_solve_kernel<1024, 1>;
-        if (nt <= 640) k = minb >= 3 ? traj_solve_kernel<640, 3> : (minb == 2 ? traj_solve_kernel<640, 2> : traj_solve_kernel<640, 1>);
-        VCB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<(unsigned)nchunks, nt, smem, st>>>(p);
-        count_launch();
-        VCB_CUDA(cudaGetLastError());
+        switch ((Ds + 7) / 8) {
+            case 1: rc = launch_tiled<1>(p, nchunks, st); break;
+            case 2: rc = launch_tiled<2>(p, nchunks, st); break;
+            case 3: rc = launch_tiled<3>(p, nchunks, st); break;
+            case 4: rc = launch_tiled<4>(p, nchunks, st); break;
+            case 5: rc = launch_tiled<5>(p, nchunks, st); break;
+            default: rc = launch_tiled<6>(p, nchunks, st); break;
+        }
     }
     cudaFreeAsync(dE, st);
     cudaFreeAsync(dG, st);
     cudaFreeAsync(dL, st);
     cudaFreeAsync(dZ, st);
     cudaFreeAsync(derr, st);
-    return VCB_OK;
+    return rc;
 }
 
 }  // namespace vcb
