@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""Runs one path of the library a few times (for ncu / quick timing): traj | dtw | fbf | argmax."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import vcb200 as vcb
+
+which = sys.argv[1]
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+vcb.set_device(0)
+def timeit(fn):
+    for _ in range(2): fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(reps): fn()
+    e.record(); torch.cuda.synchronize()
+    return s.elapsed_time(e) / reps
+if which == "traj":
+    n = int(os.environ.get("N_UTT", 1000)); limit = int(os.environ.get("LIMIT", 500))
+    gm, fm, off = vcb.synth.config_c2(n, 500)
+    t = vcb.TrajectoryGMMMap(vcb.GMMMap(*gm), limit)
+    d = torch.from_numpy(np.ascontiguousarray(fm.T)).cuda()
+    ms = timeit(lambda: vcb.vc_batch(t, d, off, _split=False))
+    print(f"traj C2 n={n} limit={limit}: {ms:.3f} ms  {n*500/ms*1e3:.3e} frames/s")
+elif which == "dtw":
+    tm, to, sq, so = vcb.synth.config_c3(int(os.environ.get("N_PAIRS", 1000)))
+    a = torch.from_numpy(np.ascontiguousarray(tm.T)).cuda(); b = torch.from_numpy(np.ascontiguousarray(sq.T)).cuda()
+    d = vcb.DTWs.DTW(fstep=0, bstep=2)
+    ms = timeit(lambda: vcb.DTWs.fit_batch(d, a, to, b, so))
+    cells = float(np.sum(np.diff(to).astype(float) * np.diff(so)))
+    print(f"dtw C3: {ms:.3f} ms  {cells/ms*1e3:.3e} cells/s")
+elif which in ("fbf", "fbf_simt"):
+    vcb.set_kernel_variant(1 if which == "fbf_simt" else 0)
+    gm, fm = vcb.synth.config_c1(int(os.environ.get("FRAMES", 1000000)))
+    g = vcb.GMMMap(*gm)
+    d = torch.from_numpy(np.ascontiguousarray(fm.T)).cuda()
+    ms = timeit(lambda: vcb.vc(g, d))
+    print(f"{which} C1: {ms:.3f} ms  {fm.shape[1]/ms*1e3:.3e} frames/s")

@@ -73,12 +73,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-    return v;
-}
-
 struct TrajParams {
     const double* P;        // [M][D2*D2] symmetric precision blocks
     const int32_t* mhat;    // [total] 0-based
@@ -113,10 +107,13 @@ __device__ __forceinline__ void tile_xyt(double (&c)[TS][TS], const double* __re
 
 // One CTA (64 threads = 8 x 8 grid of TS x TS register tiles) per chunk; Ds <= DSP = 8*TS, the
 // padding rows/columns carry a unit diagonal so the factorisation is unaffected.
+// Shared-memory plan (column-major blocks, LD = DSP+1): G2 | G1[2] | W[3] where the W buffer of
+// step t first stages R[t][t-2], then holds Tm, and finally Linv_t.
 template <int TS>
-__global__ void __launch_bounds__(64, (TS <= 3) ? 5 : ((TS == 4) ? 3 : 1))
+__global__ void __launch_bounds__(64, (TS <= 3) ? 7 : ((TS == 4) ? 4 : 2))
 traj_solve_tiled(const TrajParams p) {
     constexpr int DSP = 8 * TS, LD = DSP + 1, BS = DSP * LD;
+    constexpr int VEC = (4 * TS + 5) * DSP + 2 * TS * TS;
     const int Ds = p.Ds, D2 = 2 * Ds, BB = Ds * Ds;
     const int tid = threadIdx.x;
     const int ti = tid & 7, tj = tid >> 3, i0 = ti * TS, j0 = tj * TS;
@@ -125,64 +122,72 @@ traj_solve_tiled(const TrajParams p) {
     if (T <= 0) return;
 
     extern __shared__ __align__(16) double sm[];
-    double* Rt1 = sm;                 // R[t][t-1], overwritten in place by Tm
-    double* Rt2 = Rt1 + BS;           // R[t][t-2]
-    double* G2 = Rt2 + BS;            // L[t][t-2]
-    double* gbuf[2] = {G2 + BS, G2 + 2 * BS};                       // L[t][t-1] / L[t-1][t-2]
-    double* ibuf[3] = {G2 + 3 * BS, G2 + 4 * BS, G2 + 5 * BS};      // Linv_t, Linv_{t-1}, Linv_{t-2}
-    double* vec = G2 + 6 * BS;
-    double* colb[2] = {vec, vec + DSP};
-    double* wrowb[2] = {vec + 2 * DSP, vec + 3 * DSP};
-    double* rv = vec + 4 * DSP;
-    double* tmpv = vec + 5 * DSP;
-    double* zb[3] = {vec + 6 * DSP, vec + 7 * DSP, vec + 8 * DSP};
-    for (int e = tid; e < 8 * BS + 9 * DSP; e += 64) sm[e] = 0.0;
+    double* const G2 = sm;
+    double* const vec = sm + 6 * BS;
+    double* const lcol = vec;                       // [2][DSP][TS]   panel of L, by block parity
+    double* const xrow = vec + 2 * DSP * TS;        // [2][TS][DSP]   rows of L^-1
+    double* const dinvb = vec + 4 * DSP * TS;       // [2][TS][TS]    inverse of the diagonal tile
+    double* const rv = dinvb + 2 * TS * TS;
+    double* const tmpv = rv + DSP;
+    double* const zb = tmpv + DSP;                  // [3][DSP]
+    for (int e = tid; e < 6 * BS + VEC; e += 64) sm[e] = 0.0;
 
     const int32_t* mh = p.mhat + c0;
     const double* gv = p.Gv + c0 * D2;
     double* Lst = p.Lst + c0 * 3 * BB;
     double* Zg = p.Z + c0 * Ds;
+    const int estep_i = 64 % Ds, estep_j = 64 / Ds;   // element walk e -> e + 64 without divisions
     __syncthreads();
 
     // =========================== forward: block Cholesky + L z = r ===========================
     for (int t = 0; t < T; ++t) {
-        double* G1 = gbuf[t & 1];
-        const double* Lt1t2 = gbuf[(t & 1) ^ 1];
-        double* W = ibuf[t % 3];
-        const double* Lm1inv = ibuf[(t + 2) % 3];
-        const double* Lm2inv = ibuf[(t + 1) % 3];
-        double* zt = zb[t % 3];
-        const double* z1 = zb[(t + 2) % 3];
-        const double* z2 = zb[(t + 1) % 3];
+        double* const G1 = sm + (1 + (t & 1)) * BS;
+        const double* const Lt1t2 = sm + (1 + ((t & 1) ^ 1)) * BS;
+        double* const W = sm + (3 + t % 3) * BS;
+        const double* const Lm1inv = sm + (3 + (t + 2) % 3) * BS;
+        const double* const Lm2inv = sm + (3 + (t + 1) % 3) * BS;
+        double* const zt = zb + (t % 3) * DSP;
+        const double* const z1 = zb + ((t + 2) % 3) * DSP;
+        const double* const z2 = zb + ((t + 1) % 3) * DSP;
         const double* Pt = p.P + (size_t)mh[t] * D2 * D2;
         const double* Pm = (t >= 1) ? p.P + (size_t)mh[t - 1] * D2 * D2 : nullptr;
         const double* Pp = (t + 1 < T) ? p.P + (size_t)mh[t + 1] * D2 * D2 : nullptr;
 
-        // ---- 0. own tile of R[t][t] straight into the S accumulators (loads overlap steps 1-3);
-        //         R[t][t-1], R[t][t-2] and r_t staged column-major in shared memory
-        double s[TS][TS];
+        // ---- 0. own tiles of R[t][t] (-> S accumulators) and R[t][t-1] straight from L2 into
+        //         registers; R[t][t-2] and r_t staged in shared memory
+        double s[TS][TS], r1[TS][TS];
 #pragma unroll
         for (int x = 0; x < TS; ++x)
 #pragma unroll
             for (int y = 0; y < TS; ++y) {
                 const int i = i0 + x, j = j0 + y;
-                double v = (i == j) ? 1.0 : 0.0;
+                double v = (i == j) ? 1.0 : 0.0, u = 0.0;
                 if (i < Ds && j < Ds) {
                     v = Pt[i + (size_t)j * D2];
-                    if (Pm) v = fma(0.25, Pm[(Ds + i) + (size_t)(Ds + j) * D2], v);
+                    if (Pm) {
+                        v = fma(0.25, Pm[(Ds + i) + (size_t)(Ds + j) * D2], v);
+                        u = 0.5 * Pm[(Ds + i) + (size_t)j * D2] - 0.5 * Pt[i + (size_t)(Ds + j) * D2];
+                    }
                     if (Pp) v = fma(0.25, Pp[(Ds + i) + (size_t)(Ds + j) * D2], v);
                 }
                 s[x][y] = v;
+                r1[x][y] = u;
             }
-        for (int e = tid; e < BB; e += 64) {
-            const int j = e / Ds, i = e - j * Ds;
-            double rt1 = 0.0, rt2 = 0.0;
-            if (Pm) {
-                rt1 = 0.5 * Pm[(Ds + i) + (size_t)j * D2] - 0.5 * Pt[i + (size_t)(Ds + j) * D2];
-                if (t >= 2) rt2 = -0.25 * Pm[(Ds + i) + (size_t)(Ds + j) * D2];
+        if (t >= 2) {
+            // the W buffer still holds Linv_{t-3}, whose padding diagonal is 1: clear the padding
+            if (Ds < DSP) {
+#pragma unroll
+                for (int x = 0; x < TS; ++x)
+#pragma unroll
+                    for (int y = 0; y < TS; ++y)
+                        if (i0 + x >= Ds || j0 + y >= Ds) W[(j0 + y) * LD + i0 + x] = 0.0;
             }
-            Rt1[j * LD + i] = rt1;
-            Rt2[j * LD + i] = rt2;
+            int i = tid % Ds, j = tid / Ds;
+            for (int e = tid; e < BB; e += 64) {
+                W[j * LD + i] = -0.25 * Pm[(Ds + i) + (size_t)(Ds + j) * D2];
+                i += estep_i; j += estep_j;
+                if (i >= Ds) { i -= Ds; ++j; }
+            }
         }
         if (tid < DSP) {
             double r = 0.0;
@@ -198,31 +203,24 @@ traj_solve_tiled(const TrajParams p) {
         // ---- 1. G2 = L[t][t-2] = R[t][t-2] * Linv_{t-2}'
         {
             double c[TS][TS] = {};
-            if (t >= 2) tile_xyt<TS, LD, false>(c, Rt2, Lm2inv, i0, j0, ktri);
+            if (t >= 2) tile_xyt<TS, LD, false>(c, W, Lm2inv, i0, j0, ktri);
 #pragma unroll
             for (int y = 0; y < TS; ++y)
 #pragma unroll
                 for (int x = 0; x < TS; ++x) G2[(j0 + y) * LD + i0 + x] = c[x][y];
         }
         __syncthreads();
-        // ---- 2. Tm = R[t][t-1] - G2 * L[t-1][t-2]'   (in place, every thread owns its tile)
-        if (t >= 2) {
-            double c[TS][TS];
+        // ---- 2. Tm = R[t][t-1] - G2 * L[t-1][t-2]'  (into the W buffer; R[t][t-2] is dead)
+        if (t >= 2) tile_xyt<TS, LD, true>(r1, G2, Lt1t2, i0, j0, DSP);
 #pragma unroll
-            for (int y = 0; y < TS; ++y)
+        for (int y = 0; y < TS; ++y)
 #pragma unroll
-                for (int x = 0; x < TS; ++x) c[x][y] = Rt1[(j0 + y) * LD + i0 + x];
-            tile_xyt<TS, LD, true>(c, G2, Lt1t2, i0, j0, DSP);
-#pragma unroll
-            for (int y = 0; y < TS; ++y)
-#pragma unroll
-                for (int x = 0; x < TS; ++x) Rt1[(j0 + y) * LD + i0 + x] = c[x][y];
-        }
+            for (int x = 0; x < TS; ++x) W[(j0 + y) * LD + i0 + x] = r1[x][y];
         __syncthreads();
         // ---- 3. G1 = L[t][t-1] = Tm * Linv_{t-1}'
         {
             double c[TS][TS] = {};
-            if (t >= 1) tile_xyt<TS, LD, false>(c, Rt1, Lm1inv, i0, j0, ktri);
+            if (t >= 1) tile_xyt<TS, LD, false>(c, W, Lm1inv, i0, j0, ktri);
 #pragma unroll
             for (int y = 0; y < TS; ++y)
 #pragma unroll
@@ -232,48 +230,122 @@ traj_solve_tiled(const TrajParams p) {
         // ---- 4. S = R[t][t] - G2 G2' - G1 G1'
         if (t >= 2) tile_xyt<TS, LD, true>(s, G2, G2, i0, j0, DSP);
         if (t >= 1) tile_xyt<TS, LD, true>(s, G1, G1, i0, j0, DSP);
-        // ---- 5. right-looking Cholesky of S fused with W <- L^-1; S and W tiles stay in
-        //         registers, column k of S and row k of W are broadcast through shared memory
+        // ---- 5. blocked right-looking Cholesky of S fused with W <- L^-1.  S and W tiles stay in
+        //         registers; per block column: the diagonal tile is factorised and inverted by its
+        //         owner, the panel and the matching rows of L^-1 are formed with that inverse and
+        //         broadcast through shared memory, then every trailing tile takes a TS-rank update.
         double w[TS][TS];
 #pragma unroll
         for (int x = 0; x < TS; ++x)
 #pragma unroll
             for (int y = 0; y < TS; ++y) w[x][y] = (i0 + x == j0 + y) ? 1.0 : 0.0;
 #pragma unroll
-        for (int k = 0; k < DSP; ++k) {
-            constexpr int dummy = 0; (void)dummy;
-            const int kt = k / TS, kb = k % TS;
-            double* col = colb[k & 1];
-            double* wrow = wrowb[k & 1];
-            if (tj == kt) {
+        for (int kb = 0; kb < 8; ++kb) {
+            double* const dv = dinvb + (kb & 1) * TS * TS;
+            double* const lc = lcol + (kb & 1) * DSP * TS;
+            double* const xr = xrow + (kb & 1) * TS * DSP;
+            if (ti == kb && tj == kb) {
+                double di[TS];
 #pragma unroll
-                for (int x = 0; x < TS; ++x) col[i0 + x] = s[x][kb];
-            }
-            if (ti == kt) {
+                for (int c = 0; c < TS; ++c) {
+                    const double d = s[c][c];
+                    if (!(d > 0.0)) atomicExch(p.err, 1);
+                    di[c] = rsqrt(d);
+                    s[c][c] = d * di[c];
 #pragma unroll
-                for (int y = 0; y < TS; ++y) wrow[j0 + y] = w[kb][y];
-            }
-            __syncthreads();
-            const double skk = col[k];
-            if (!(skk > 0.0) && tid == 0) atomicExch(p.err, 1);
-            const double dinv = rsqrt(skk);
-            double li[TS], lj[TS], xj[TS];
+                    for (int r = c + 1; r < TS; ++r) s[r][c] *= di[c];
 #pragma unroll
-            for (int x = 0; x < TS; ++x) li[x] = col[i0 + x] * dinv;
+                    for (int r = c + 1; r < TS; ++r)
 #pragma unroll
-            for (int y = 0; y < TS; ++y) { lj[y] = col[j0 + y] * dinv; xj[y] = wrow[j0 + y] * dinv; }
+                        for (int c2 = c + 1; c2 <= r; ++c2) s[r][c2] = fma(-s[r][c], s[c2][c], s[r][c2]);
+                }
+                double inv[TS][TS];
 #pragma unroll
-            for (int x = 0; x < TS; ++x)
+                for (int c = 0; c < TS; ++c) {
 #pragma unroll
-                for (int y = 0; y < TS; ++y) {
-                    const int i = i0 + x, j = j0 + y;
-                    if (i > k) {
-                        if (j > k) s[x][y] = fma(-li[x], lj[y], s[x][y]);
-                        else w[x][y] = fma(-li[x], xj[y], w[x][y]);
-                    } else if (i == k && j <= k) {
-                        w[x][y] = xj[y];
+                    for (int r = 0; r < TS; ++r) inv[r][c] = 0.0;
+                    inv[c][c] = di[c];
+#pragma unroll
+                    for (int r = c + 1; r < TS; ++r) {
+                        double a = 0.0;
+#pragma unroll
+                        for (int k = c; k < r; ++k) a = fma(s[r][k], inv[k][c], a);
+                        inv[r][c] = -a * di[r];
                     }
                 }
+#pragma unroll
+                for (int r = 0; r < TS; ++r)
+#pragma unroll
+                    for (int c = 0; c < TS; ++c) dv[r * TS + c] = inv[r][c];
+            }
+            __syncthreads();
+            if (tj == kb && ti > kb) {        // panel: L = S_tile * Dinv'
+                double dl[TS][TS], o[TS][TS];
+#pragma unroll
+                for (int r = 0; r < TS; ++r)
+#pragma unroll
+                    for (int c = 0; c < TS; ++c) dl[r][c] = dv[r * TS + c];
+#pragma unroll
+                for (int x = 0; x < TS; ++x)
+#pragma unroll
+                    for (int y = 0; y < TS; ++y) {
+                        double a = 0.0;
+#pragma unroll
+                        for (int c = 0; c <= y; ++c) a = fma(s[x][c], dl[y][c], a);
+                        o[x][y] = a;
+                    }
+#pragma unroll
+                for (int x = 0; x < TS; ++x)
+#pragma unroll
+                    for (int y = 0; y < TS; ++y) { s[x][y] = o[x][y]; lc[(i0 + x) * TS + y] = o[x][y]; }
+            }
+            if (ti == kb && tj <= kb) {       // rows of L^-1: X = Dinv * W_tile
+                double dl[TS][TS], o[TS][TS];
+#pragma unroll
+                for (int r = 0; r < TS; ++r)
+#pragma unroll
+                    for (int c = 0; c < TS; ++c) dl[r][c] = dv[r * TS + c];
+#pragma unroll
+                for (int x = 0; x < TS; ++x)
+#pragma unroll
+                    for (int y = 0; y < TS; ++y) {
+                        double a = 0.0;
+#pragma unroll
+                        for (int c = 0; c <= x; ++c) a = fma(dl[x][c], w[c][y], a);
+                        o[x][y] = a;
+                    }
+#pragma unroll
+                for (int x = 0; x < TS; ++x)
+#pragma unroll
+                    for (int y = 0; y < TS; ++y) { w[x][y] = o[x][y]; xr[x * DSP + j0 + y] = o[x][y]; }
+            }
+            __syncthreads();
+            if (ti > kb) {
+                double li[TS][TS];
+#pragma unroll
+                for (int x = 0; x < TS; ++x)
+#pragma unroll
+                    for (int c = 0; c < TS; ++c) li[x][c] = lc[(i0 + x) * TS + c];
+                if (tj > kb) {
+#pragma unroll
+                    for (int y = 0; y < TS; ++y)
+#pragma unroll
+                        for (int c = 0; c < TS; ++c) {
+                            const double ljv = lc[(j0 + y) * TS + c];
+#pragma unroll
+                            for (int x = 0; x < TS; ++x) s[x][y] = fma(-li[x][c], ljv, s[x][y]);
+                        }
+                } else {
+#pragma unroll
+                    for (int y = 0; y < TS; ++y)
+#pragma unroll
+                        for (int c = 0; c < TS; ++c) {
+                            const double xv = xr[c * DSP + j0 + y];
+#pragma unroll
+                            for (int x = 0; x < TS; ++x) w[x][y] = fma(-li[x][c], xv, w[x][y]);
+                        }
+                }
+            }
         }
 #pragma unroll
         for (int y = 0; y < TS; ++y)
@@ -308,11 +380,13 @@ traj_solve_tiled(const TrajParams p) {
         // ---- 7. stream the three blocks of block-row t to HBM (row-major, compact)
         {
             double* dst = Lst + (size_t)t * 3 * BB;
+            int j = tid % Ds, i = tid / Ds;
             for (int e = tid; e < BB; e += 64) {
-                const int i = e / Ds, j = e - i * Ds;
                 dst[e] = W[j * LD + i];
                 dst[BB + e] = G1[j * LD + i];
                 dst[2 * BB + e] = G2[j * LD + i];
+                j += estep_i; i += estep_j;
+                if (j >= Ds) { j -= Ds; ++i; }
             }
         }
         __syncthreads();
@@ -320,22 +394,20 @@ traj_solve_tiled(const TrajParams p) {
 
     // =========================== backward: L' y = z ===========================================
     // y_t = Linv_t' (z_t - L[t+1][t]' y_{t+1} - L[t+2][t]' y_{t+2});  thread = output row j
-    double* bb[2][3] = {{sm, sm + BB, sm + 2 * BB}, {sm + 3 * BB, sm + 4 * BB, sm + 5 * BB}};
-    double* yb[3] = {zb[0], zb[1], zb[2]};
     const bool vec_ok = (BB % 2) == 0;
     auto prefetch = [&](int t, int buf) {
         const int n16 = BB / 2;  // 16-byte pieces per block
         for (int e = tid; e < 3 * n16; e += 64) {
             const int b = e / n16, o = e - b * n16;
-            if (t + b < T) cp_async16(bb[buf][b] + 2 * o, Lst + ((size_t)(t + b) * 3 + b) * BB + 2 * o);
+            if (t + b < T) cp_async16(sm + (buf * 3 + b) * BB + 2 * o, Lst + ((size_t)(t + b) * 3 + b) * BB + 2 * o);
         }
     };
     if (vec_ok) { prefetch(T - 1, (T - 1) & 1); cp_async_commit(); }
     for (int t = T - 1; t >= 0; --t) {
         const int buf = t & 1;
-        double* yt = yb[t % 3];
-        const double* y1 = yb[(t + 1) % 3];
-        const double* y2 = yb[(t + 2) % 3];
+        double* const yt = zb + (t % 3) * DSP;
+        const double* const y1 = zb + ((t + 1) % 3) * DSP;
+        const double* const y2 = zb + ((t + 2) % 3) * DSP;
         if (vec_ok) {
             if (t >= 1) prefetch(t - 1, buf ^ 1);
             cp_async_commit();
@@ -343,19 +415,23 @@ traj_solve_tiled(const TrajParams p) {
         } else {
             for (int e = tid; e < 3 * BB; e += 64) {
                 const int b = e / BB, o = e - b * BB;
-                if (t + b < T) bb[buf][b][o] = Lst[((size_t)(t + b) * 3 + b) * BB + o];
+                if (t + b < T) sm[(buf * 3 + b) * BB + o] = Lst[((size_t)(t + b) * 3 + b) * BB + o];
             }
         }
         __syncthreads();
-        const double* Li = bb[buf][0];
-        const double* L1 = bb[buf][1];
-        const double* L2 = bb[buf][2];
+        const double* const Li = sm + (buf * 3 + 0) * BB;
+        const double* const L1 = sm + (buf * 3 + 1) * BB;
+        const double* const L2 = sm + (buf * 3 + 2) * BB;
         if (tid < Ds) {
             double s0 = 0.0, s1 = 0.0;
-            if (t + 1 < T)
+            if (t + 1 < T) {
+#pragma unroll 4
                 for (int i = 0; i < Ds; ++i) s0 = fma(L1[i * Ds + tid], y1[i], s0);
-            if (t + 2 < T)
+            }
+            if (t + 2 < T) {
+#pragma unroll 4
                 for (int i = 0; i < Ds; ++i) s1 = fma(L2[i * Ds + tid], y2[i], s1);
+            }
             rv[tid] = Zg[(size_t)t * Ds + tid] - (s0 + s1);
         }
         __syncthreads();
@@ -375,7 +451,7 @@ traj_solve_tiled(const TrajParams p) {
 template <int TS>
 static int32_t launch_tiled(const TrajParams& p, int64_t nchunks, cudaStream_t st) {
     constexpr int DSP = 8 * TS, LD = DSP + 1;
-    const size_t smem = ((size_t)8 * DSP * LD + 9 * DSP) * sizeof(double);
+    const size_t smem = ((size_t)6 * DSP * LD + (4 * TS + 5) * DSP + 2 * TS * TS) * sizeof(double);
     auto k = traj_solve_tiled<TS>;
     VCB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<(unsigned)nchunks, 64, smem, st>>>(p);
