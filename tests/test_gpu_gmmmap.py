@@ -63,7 +63,12 @@ def test_odd_shapes(vcb, oracle, variant, M, D):
     gm = vcb.synth.random_joint_gmm(100 + M + D, M, 2 * D, mean_scale=0.3)
     fm = vcb.synth.fbf_feature_matrix(gm, 700, 5)
     ref = oracle.GMMMap(*gm).vc(fm, nthreads=oracle.max_threads())
-    out = vcb.vc(vcb.GMMMap(*gm), fm)
+    try:
+        out = vcb.vc(vcb.GMMMap(*gm), fm)
+    except vcb.VCBError as e:
+        if variant == 2 and e.code == vcb._lib.EUNSUPPORTED:
+            pytest.skip("shape outside the tensor-core kernel's shared-memory plan (auto mode uses the CUDA-core kernel)")
+        raise
     assert np.abs(out - ref).max() <= tol_for(ref[1:])
 
 

@@ -12,16 +12,20 @@
 // 1e-4 parity bar by three orders of magnitude), so both operands are split into tf32 hi + lo
 // and each k-step issues three MMAs (hi.hi, hi.lo, lo.hi) into the same fp32 accumulator.
 //
-// Warp roles (one persistent CTA per SM, 320 threads):
-//   warps 0-3  epilogue: tcgen05.ld their 32 TMEM lanes (one frame per thread), |z|^2 -> log-lik,
-//              online soft-max, posterior-weighted accumulation of Ey (conversion) or running
-//              top-2 (arg-max).  Per-mixture means and log-likelihoods never leave the SM.
+// Warp roles (one persistent CTA per SM, 256 threads):
+//   warps 0-3  epilogue: tcgen05.ld of their 32 TMEM lanes (one frame per thread), software-
+//              pipelined over the mixtures of a chunk, |z|^2 -> log-lik, online soft-max,
+//              posterior-weighted accumulation of Ey (conversion) or running top-2 (arg-max).
+//              Per-mixture means and log-likelihoods never leave the SM.  (The code also supports
+//              two groups, one per accumulator stage, merged through shared memory.)
 //   warp 4     B producer: cp.async.bulk (TMA 1-D) of pre-packed operand images, ring of stages.
 //   warp 5     MMA issuer: one lane issues tcgen05.mma / tcgen05.commit; owns the TMEM allocation.
-//   warps 6-9  A loaders: read Float64 frames, centre in Float64, split to tf32 hi/lo, write the
+//   warps 6-7  A loaders (two frame rows per thread): read Float64 frames, centre in Float64, split to tf32 hi/lo, write the
 //              UMMA K-major (no-swizzle) image to shared memory, double-buffered across tiles.
 // Pipelines: smem B ring (full/empty), A double buffer (full/empty), TMEM accumulator double
 // buffer (full/empty) -- all mbarriers; tcgen05.commit signals the "empty"/"full" transitions.
+#include <cstdlib>
+
 #include "vcb_kernels.h"
 
 namespace vcb {
@@ -29,8 +33,14 @@ namespace vcb {
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 320;
+// One epilogue group: TMEM can be read at only ~64 B/clk/SM (measured: two groups reading both
+// accumulator stages at once halve each other's rate and leave the MMA no free stage), so a single
+// group that keeps the read port busy while the MMA fills the other stage is the better schedule.
+constexpr int kEpiGroups = 1;
+constexpr int kProducerWarp = 4 * kEpiGroups, kMmaWarp = kProducerWarp + 1, kLoaderWarp0 = kProducerWarp + 2;
+constexpr int kThreads = (kLoaderWarp0 + 2) * 32;
 constexpr int kMaxStages = 4;
+constexpr size_t kBarBytes = 1024;
 
 struct TcParams {
     const double* X; int64_t T; int64_t ldx;
@@ -41,6 +51,7 @@ struct TcParams {
     int64_t ntiles;
     double* Y; int64_t ldy; int copy_power;
     int32_t* mhat; int* flag_count; int64_t* flag_list;
+    int debug;   // timing experiments only (VCB_TC_DEBUG): 1 = B loads shrunk to 16 B, 2 = MMAs skipped
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -154,7 +165,8 @@ gmm_tc_kernel(const TcParams p) {
     uint8_t* a_smem = smem_raw;
     uint8_t* b_smem = a_smem + (size_t)AB * a_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + (size_t)S * b_bytes);
-    // bars: a_full[2], a_empty[2], acc_full[2], acc_empty[2], b_full[kMaxStages], b_empty[kMaxStages]
+    // bars: a_full[2], a_empty[2], acc_full[2], acc_empty[2], b_full[kMaxStages], b_empty[kMaxStages],
+    //       part_full, part_empty
     const uint32_t bar0 = smem_u32(bars);
     auto a_full = [&](int i) { return bar0 + 8u * i; };
     auto a_empty = [&](int i) { return bar0 + 8u * (2 + i); };
@@ -162,19 +174,24 @@ gmm_tc_kernel(const TcParams p) {
     auto acc_empty = [&](int i) { return bar0 + 8u * (6 + i); };
     auto b_full = [&](int i) { return bar0 + 8u * (8 + i); };
     auto b_empty = [&](int i) { return bar0 + 8u * (8 + kMaxStages + i); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * kMaxStages);
+    const uint32_t part_full = bar0 + 8u * (8 + 2 * kMaxStages);
+    const uint32_t part_empty = bar0 + 8u * (9 + 2 * kMaxStages);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * kMaxStages);
+    float* part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes);  // [PART_ROWS][128]
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(a_full(i), 128);
+            mbar_init(a_full(i), 64);
             mbar_init(a_empty(i), 1);
             mbar_init(acc_full(i), 1);
             mbar_init(acc_empty(i), 128);
         }
         for (int i = 0; i < kMaxStages; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
+        mbar_init(part_full, 128);
+        mbar_init(part_empty, 128);
         fence_barrier_init();
     }
-    if (warp == 5) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -182,7 +199,7 @@ gmm_tc_kernel(const TcParams p) {
 
     const int64_t my_tiles = (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
 
-    if (warp == 4) {
+    if (warp == kProducerWarp) {
         // ======================= B producer =======================
         if (lane == 0) {
             const int64_t total = my_tiles * NCH;
@@ -191,11 +208,12 @@ gmm_tc_kernel(const TcParams p) {
                 const uint32_t ph = (uint32_t)((it / S) & 1);
                 const int c = (int)(it % NCH);
                 mbar_wait(b_empty(s), ph ^ 1);
-                mbar_expect_tx(b_full(s), b_bytes);
-                bulk_g2s(smem_u32(b_smem + (size_t)s * b_bytes), p.B + (size_t)c * 2 * N * KP, b_bytes, b_full(s));
+                const uint32_t nbytes = (p.debug == 1) ? 16u : b_bytes;
+                mbar_expect_tx(b_full(s), nbytes);
+                bulk_g2s(smem_u32(b_smem + (size_t)s * b_bytes), p.B + (size_t)c * 2 * N * KP, nbytes, b_full(s));
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == kMmaWarp) {
         // ======================= MMA issuer =======================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(kTileM, N);
@@ -206,7 +224,6 @@ gmm_tc_kernel(const TcParams p) {
                 const uint32_t aph = (uint32_t)((tl / AB) & 1);
                 mbar_wait(a_full(ab), aph);
                 const uint32_t a_hi = smem_u32(a_smem + (size_t)ab * a_bytes);
-                const uint32_t a_lo = a_hi + a_half;
                 for (int c = 0; c < NCH; ++c, ++it) {
                     const int s = (int)(it % S);
                     const uint32_t ph = (uint32_t)((it / S) & 1);
@@ -215,18 +232,23 @@ gmm_tc_kernel(const TcParams p) {
                     mbar_wait(b_full(s), ph);
                     mbar_wait(acc_empty(acc), accph ^ 1);
                     tc_fence_after();
+                    // Descriptors differ from their k-step-0 value only in the start-address field
+                    // (low word), which advances by two 16-byte K slices per k-step.  Issuing is
+                    // the scarce resource here (one thread, ~70 cycles per tcgen05.mma), so the
+                    // loop body is nothing but three MMAs and four 32-bit adds.
                     const uint32_t b_hi = smem_u32(b_smem + (size_t)s * b_bytes);
-                    const uint32_t b_lo = b_hi + b_half;
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
-                    for (int kk = 0; kk < ksteps; ++kk) {
-                        // one k-step = 8 tf32 = two 16-byte K slices
-                        const uint32_t aoff = (uint32_t)kk * 2u * (kTileM * 16u);
-                        const uint32_t boff = (uint32_t)kk * 2u * ((uint32_t)N * 16u);
-                        const uint64_t dah = make_desc(a_hi + aoff, kTileM * 16u, 128u);
-                        const uint64_t dal = make_desc(a_lo + aoff, kTileM * 16u, 128u);
-                        const uint64_t dbh = make_desc(b_hi + boff, (uint32_t)N * 16u, 128u);
-                        const uint64_t dbl = make_desc(b_lo + boff, (uint32_t)N * 16u, 128u);
-                        umma_tf32(d_tmem, dal, dbh, idesc, kk > 0 ? 1u : 0u);  // small terms first
+                    uint64_t dah = make_desc(a_hi, kTileM * 16u, 128u);
+                    uint64_t dal = make_desc(a_hi + a_half, kTileM * 16u, 128u);
+                    uint64_t dbh = make_desc(b_hi, (uint32_t)N * 16u, 128u);
+                    uint64_t dbl = make_desc(b_hi + b_half, (uint32_t)N * 16u, 128u);
+                    const uint64_t astep = (2u * (kTileM * 16u)) >> 4, bstep = (2u * ((uint32_t)N * 16u)) >> 4;
+                    umma_tf32(d_tmem, dal, dbh, idesc, 0u);  // small terms first; first MMA overwrites
+                    umma_tf32(d_tmem, dah, dbl, idesc, 1u);
+                    umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+                    for (int kk = 1; kk < (p.debug == 2 ? 0 : ksteps); ++kk) {
+                        dah += astep; dal += astep; dbh += bstep; dbl += bstep;
+                        umma_tf32(d_tmem, dal, dbh, idesc, 1u);
                         umma_tf32(d_tmem, dah, dbl, idesc, 1u);
                         umma_tf32(d_tmem, dah, dbh, idesc, 1u);
                     }
@@ -236,130 +258,227 @@ gmm_tc_kernel(const TcParams p) {
                 }
             }
         }
-    } else if (warp >= 6) {
-        // ======================= A loaders (128 threads, one frame row each) =======================
-        const int row = threadIdx.x - 6 * 32;
-        const uint32_t row_off = (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
+    } else if (warp >= kLoaderWarp0) {
+        // ======================= A loaders (64 threads, two frame rows each) =======================
+        const int row0 = threadIdx.x - kLoaderWarp0 * 32;
         for (int64_t tl = 0; tl < my_tiles; ++tl) {
             const int ab = (int)(tl % AB);
             const uint32_t aph = (uint32_t)((tl / AB) & 1);
             const int64_t tile = blockIdx.x + tl * gridDim.x;
-            const int64_t t = tile * kTileM + row;
             mbar_wait(a_empty(ab), aph ^ 1);
             uint8_t* hi = a_smem + (size_t)ab * a_bytes;
             uint8_t* lo = hi + a_half;
-            const bool live = t < p.T;
-            const double* x = p.X + (live ? t : 0) * p.ldx;
-            for (int k4 = 0; k4 < KP / 4; ++k4) {
-                float4 h, l;
-                float* hp = &h.x;
-                float* lp = &l.x;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int k = 4 * k4 + j;
-                    double v = 0.0;
-                    if (live && k < p.D) v = x[k] - p.xbar[k];
-                    else if (k == p.D) v = 1.0;
-                    const float fh = to_tf32((float)v);
-                    hp[j] = fh;
-                    lp[j] = to_tf32((float)(v - (double)fh));
+            for (int h = 0; h < 2; ++h) {
+                const int row = row0 + 64 * h;
+                const uint32_t row_off = (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
+                const int64_t t = tile * kTileM + row;
+                const bool live = t < p.T;
+                const double* x = p.X + (live ? t : 0) * p.ldx;
+                for (int k4 = 0; k4 < KP / 4; ++k4) {
+                    float4 hv, lv;
+                    float* hp = &hv.x;
+                    float* lp = &lv.x;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int k = 4 * k4 + j;
+                        double v = 0.0;
+                        if (live && k < p.D) v = x[k] - p.xbar[k];
+                        else if (k == p.D) v = 1.0;
+                        const float fh = to_tf32((float)v);
+                        hp[j] = fh;
+                        lp[j] = to_tf32((float)(v - (double)fh));
+                    }
+                    const uint32_t off = (uint32_t)k4 * (kTileM * 16u) + row_off;
+                    *reinterpret_cast<float4*>(hi + off) = hv;
+                    *reinterpret_cast<float4*>(lo + off) = lv;
                 }
-                const uint32_t off = (uint32_t)k4 * (kTileM * 16u) + row_off;
-                *reinterpret_cast<float4*>(hi + off) = h;
-                *reinterpret_cast<float4*>(lo + off) = l;
             }
             fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
             mbar_arrive(a_full(ab));
         }
     } else {
-        // ======================= epilogue (warps 0-3; thread = frame = TMEM lane) =======================
-        const int row = threadIdx.x;  // 0..127
-        const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+        // ======================= epilogue (warps 0-7; thread = frame = TMEM lane) =======================
+        const int group = warp >> 2;          // with two groups: the accumulator stage this group drains
+        const int row = threadIdx.x & 127;    // 0..127
+        const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
+        constexpr int LOADW = (ROWS <= 64) ? ROWS : 32;   // TMEM columns fetched per wait
         int64_t it = 0;
         for (int64_t tl = 0; tl < my_tiles; ++tl) {
             const int64_t tile = blockIdx.x + tl * gridDim.x;
             const int64_t t = tile * kTileM + row;
             float mx = -INFINITY, sum = 0.f, second = -INFINITY, qbest = 0.f;
-            int best = 0;
+            int best = 0x7FFFFFFF;
             float y[CONVERT ? DP : 1];
             if (CONVERT) {
 #pragma unroll
                 for (int r = 0; r < DP; ++r) y[r] = 0.f;
             }
             for (int c = 0; c < NCH; ++c, ++it) {
+                if (kEpiGroups == 2 && (int)(it & 1) != group) continue;
                 const int acc = (int)(it & 1);
                 const uint32_t accph = (uint32_t)((it >> 1) & 1);
                 mbar_wait(acc_full(acc), accph);
                 tc_fence_after();
                 const uint32_t tcol = tmem_base + lane_base + (uint32_t)(acc * N);
+                if (ROWS <= 64) {
+                    // Software pipeline over the mixtures of this chunk: the TMEM loads of mixture
+                    // g+1 are in flight while mixture g is reduced (tcgen05.wait::ld waits for all
+                    // outstanding loads, so the wait sits after the compute).
+                    auto fetch = [&](float (&v)[LOADW], int g) {
+                        const uint32_t mcol = tcol + (uint32_t)(g * ROWS);
+#pragma unroll
+                        for (int r = 0; r < ROWS; r += 8) tmem_ld8(mcol + r, v + r);
+                    };
+                    auto reduce = [&](const float (&v)[LOADW], int g) {
+                        const int m = c * p.G + g;
+                        const float cm = p.cst[m];  // -inf for padding mixtures
+                        float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+                        for (int r = 0; r < DP; r += 4) {
+                            q0 = fmaf(v[r], v[r], q0);
+                            q1 = fmaf(v[r + 1], v[r + 1], q1);
+                            q2 = fmaf(v[r + 2], v[r + 2], q2);
+                            q3 = fmaf(v[r + 3], v[r + 3], q3);
+                        }
+                        const float q = (q0 + q1) + (q2 + q3);
+                        const float l = fmaf(-0.5f, q, cm);
+                        if (CONVERT) {
+                            if (l > mx) {
+                                const float a = __expf(mx - l);
+                                sum *= a;
+#pragma unroll
+                                for (int r = 0; r < DP; ++r) y[r] *= a;
+                                mx = l;
+                            }
+                            const float w = (l == -INFINITY) ? 0.f : __expf(l - mx);
+                            sum += w;
+#pragma unroll
+                            for (int r = 0; r < DP; ++r) y[r] = fmaf(w, v[(CONVERT ? DP : 0) + r], y[r]);
+                        } else {
+                            if (l > mx) { second = mx; mx = l; best = m; qbest = q; }
+                            else if (l > second) second = l;
+                        }
+                    };
+                    float v0[LOADW], v1[LOADW];
+                    fetch(v0, 0);
+                    tmem_ld_wait();
+                    for (int g = 0; g < p.G; g += 2) {
+                        if (g + 1 < p.G) fetch(v1, g + 1);
+                        reduce(v0, g);
+                        tmem_ld_wait();
+                        if (g + 1 < p.G) {
+                            if (g + 2 < p.G) fetch(v0, g + 2);
+                            reduce(v1, g + 1);
+                            tmem_ld_wait();
+                        }
+                    }
+                } else {
                 for (int g = 0; g < p.G; ++g) {
                     const int m = c * p.G + g;
                     const uint32_t mcol = tcol + (uint32_t)(g * ROWS);
-                    // ---- |z|^2 over the DP whitening columns
-                    float q = 0.f;
-#pragma unroll
-                    for (int r0 = 0; r0 < DP; r0 += 32) {
-                        float v[32];
-#pragma unroll
-                        for (int r = 0; r < 32; r += 8)
-                            if (r0 + r < DP) tmem_ld8(mcol + r0 + r, v + r);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int r = 0; r < 32; ++r)
-                            if (r0 + r < DP) q = fmaf(v[r], v[r], q);
-                    }
-                    const float l = fmaf(-0.5f, q, p.cst[m]);  // -inf for padding mixtures
-                    if (CONVERT) {
-                        if (l > mx) {
-                            const float a = __expf(mx - l);
-                            sum *= a;
-#pragma unroll
-                            for (int r = 0; r < DP; ++r) y[r] *= a;
-                            mx = l;
-                        }
-                        const float w = (l == -INFINITY) ? 0.f : __expf(l - mx);
-                        sum += w;
+                    const float cm = p.cst[m];  // -inf for padding mixtures
+                    {
+                        float q = 0.f;
 #pragma unroll
                         for (int r0 = 0; r0 < DP; r0 += 32) {
                             float v[32];
 #pragma unroll
                             for (int r = 0; r < 32; r += 8)
-                                if (r0 + r < DP) tmem_ld8(mcol + DP + r0 + r, v + r);
+                                if (r0 + r < DP) tmem_ld8(mcol + r0 + r, v + r);
                             tmem_ld_wait();
 #pragma unroll
                             for (int r = 0; r < 32; ++r)
-                                if (r0 + r < DP) y[r0 + r] = fmaf(w, v[r], y[r0 + r]);
+                                if (r0 + r < DP) q = fmaf(v[r], v[r], q);
                         }
-                    } else {
-                        if (l > mx) { second = mx; mx = l; best = m; qbest = q; }
-                        else if (l > second) second = l;
+                        const float l = fmaf(-0.5f, q, cm);
+                        if (CONVERT) {
+                            if (l > mx) {
+                                const float a = __expf(mx - l);
+                                sum *= a;
+#pragma unroll
+                                for (int r = 0; r < DP; ++r) y[r] *= a;
+                                mx = l;
+                            }
+                            const float w = (l == -INFINITY) ? 0.f : __expf(l - mx);
+                            sum += w;
+#pragma unroll
+                            for (int r0 = 0; r0 < DP; r0 += 32) {
+                                float v[32];
+#pragma unroll
+                                for (int r = 0; r < 32; r += 8)
+                                    if (r0 + r < DP) tmem_ld8(mcol + DP + r0 + r, v + r);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int r = 0; r < 32; ++r)
+                                    if (r0 + r < DP) y[r0 + r] = fmaf(w, v[r], y[r0 + r]);
+                            }
+                        } else {
+                            if (l > mx) { second = mx; mx = l; best = m; qbest = q; }
+                            else if (l > second) second = l;
+                        }
                     }
+                }
                 }
                 tc_fence_before();
                 mbar_arrive(acc_empty(acc));
             }
-            if (t < p.T) {
+            // ---- merge the two groups' partial states of this tile (group 1 -> smem -> group 0)
+            const uint32_t pph = (uint32_t)(tl & 1);
+            if (kEpiGroups == 2 && group == 1) {
+                mbar_wait(part_empty, pph ^ 1);
+                part[0 * 128 + row] = mx;
                 if (CONVERT) {
-                    const float inv = 1.0f / sum;
-                    double* yo = p.Y + t * p.ldy;
+                    part[1 * 128 + row] = sum;
 #pragma unroll
-                    for (int r = 0; r < DP; ++r)
-                        if (r < p.D) yo[r] = (double)(y[r] * inv);
-                    if (p.copy_power) yo[-1] = p.X[t * p.ldx - 1];  // src/common.jl:23
+                    for (int r = 0; r < DP; ++r) part[(2 + r) * 128 + row] = y[r];
                 } else {
-                    p.mhat[t] = best;
-                    if (mx - second < 1e-3f * (1.0f + qbest) || !(mx == mx)) {
-                        const int slot = atomicAdd(p.flag_count, 1);
-                        p.flag_list[slot] = t;
+                    part[1 * 128 + row] = second;
+                    part[2 * 128 + row] = qbest;
+                    part[3 * 128 + row] = __int_as_float(best);
+                }
+                mbar_arrive(part_full);
+            } else {
+                if (kEpiGroups == 2) mbar_wait(part_full, pph);
+                const float mxb = (kEpiGroups == 2) ? part[0 * 128 + row] : -INFINITY;
+                if (CONVERT) {
+                    const float m2 = fmaxf(mx, mxb);
+                    const float fa = (mx == -INFINITY) ? 0.f : __expf(mx - m2);
+                    const float fb = (mxb == -INFINITY) ? 0.f : __expf(mxb - m2);
+                    const float sumb = (kEpiGroups == 2) ? part[1 * 128 + row] : 0.f;
+                    const float inv = 1.0f / (sum * fa + sumb * fb);
+                    if (t < p.T) {
+                        double* yo = p.Y + t * p.ldy;
+#pragma unroll
+                        for (int r = 0; r < DP; ++r)
+                            if (r < p.D) yo[r] = (double)((y[r] * fa + ((kEpiGroups == 2) ? part[(2 + r) * 128 + row] : 0.f) * fb) * inv);
+                        if (p.copy_power) yo[-1] = p.X[t * p.ldx - 1];  // src/common.jl:23
+                    }
+                } else {
+                    const float secb = (kEpiGroups == 2) ? part[1 * 128 + row] : -INFINITY, qb = (kEpiGroups == 2) ? part[2 * 128 + row] : 0.f;
+                    const int bestb = (kEpiGroups == 2) ? __float_as_int(part[3 * 128 + row]) : 0x7FFFFFFF;
+                    // first maximum wins on ties, like indmax (src/gmm.jl:46)
+                    const bool a_wins = (mx > mxb) || (mx == mxb && best < bestb);
+                    const float top = a_wins ? mx : mxb;
+                    const float sec = a_wins ? fmaxf(second, mxb) : fmaxf(secb, mx);
+                    const float qtop = a_wins ? qbest : qb;
+                    const int btop = a_wins ? best : bestb;
+                    if (t < p.T) {
+                        p.mhat[t] = btop;
+                        if (top - sec < 1e-3f * (1.0f + qtop) || !(top == top)) {
+                            const int slot = atomicAdd(p.flag_count, 1);
+                            p.flag_list[slot] = t;
+                        }
                     }
                 }
+                if (kEpiGroups == 2) mbar_arrive(part_empty);
             }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
@@ -405,14 +524,12 @@ int32_t dispatch_tc(int DP, const TcParams& p, size_t smem, cudaStream_t st) {
 }
 
 constexpr size_t kSmemLimit = 227 * 1024;
-constexpr size_t kBarBytes = 1024;
 
 }  // namespace
 
-TcPlan tc_plan(int M, int KP, int rows_per_mixture) {
+TcPlan tc_plan(int M, int KP, int rows_per_mixture, int part_rows) {
     TcPlan best;
-    const int dp = rows_per_mixture;  // caller passes DP or 2*DP
-    (void)dp;
+    const size_t extra = kBarBytes + (size_t)part_rows * 128 * sizeof(float);
     const int gmax = 256 / rows_per_mixture;
     if (gmax < 1) return best;
     // candidate groupings ordered by (padded mixture count, larger G first)
@@ -423,14 +540,14 @@ TcPlan tc_plan(int M, int KP, int rows_per_mixture) {
             if (n % 16) continue;
             const size_t a = (size_t)abufs * 2 * kTileM * KP * 4;
             const size_t bst = (size_t)2 * n * KP * 4;
-            if (a + 2 * bst + kBarBytes > kSmemLimit) continue;
+            if (a + 2 * bst + extra > kSmemLimit) continue;
             const int padded = (M + g - 1) / g * g;
             if (padded < best_pad) {
                 best_pad = padded;
-                int stages = (int)((kSmemLimit - kBarBytes - a) / bst);
+                int stages = (int)((kSmemLimit - extra - a) / bst);
                 if (stages > kMaxStages) stages = kMaxStages;
                 best.G = g; best.N = n; best.stages = stages; best.abufs = abufs;
-                best.smem = a + (size_t)stages * bst + kBarBytes;
+                best.smem = a + (size_t)stages * bst + extra;
             }
         }
     }
@@ -444,7 +561,7 @@ bool tc_supported(const vcb_gmmmap& g, bool convert) {
 
 static void fill_common(const vcb_gmmmap& g, const double* dX, int64_t T, int64_t ldx, bool convert, TcParams& p,
                         size_t& smem) {
-    const TcPlan plan = tc_plan(g.M, g.tc.KP, convert ? 2 * g.DP : g.DP);
+    const TcPlan plan = tc_plan(g.M, g.tc.KP, convert ? 2 * g.DP : g.DP, convert ? g.DP + 2 : 4);
     p.X = dX; p.T = T; p.ldx = ldx; p.xbar = g.d_xbar.p;
     p.B = convert ? g.tc.Bc.p : g.tc.Bw.p;
     p.cst = g.tc.cst.p;
@@ -452,6 +569,8 @@ static void fill_common(const vcb_gmmmap& g, const double* dX, int64_t T, int64_
     p.NCH = convert ? g.tc.NCHC : g.tc.NCHW;
     p.stages = plan.stages; p.abufs = plan.abufs;
     p.ntiles = (T + kTileM - 1) / kTileM;
+    static const int dbg = [] { const char* e = getenv("VCB_TC_DEBUG"); return e ? atoi(e) : 0; }();
+    p.debug = dbg;
     smem = plan.smem;
 }
 

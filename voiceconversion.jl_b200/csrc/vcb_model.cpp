@@ -227,7 +227,7 @@ int32_t build_gmmmap(const double* weights, const double* mu, const double* sigm
         vcb_tc_pack& tc = g.tc;
         const int DP = g.DP;
         tc.KP = round_up(D + 1, 8);
-        const TcPlan pc = tc_plan(M, tc.KP, 2 * DP), pw = tc_plan(M, tc.KP, DP);
+        const TcPlan pc = tc_plan(M, tc.KP, 2 * DP, DP + 2), pw = tc_plan(M, tc.KP, DP, 4);
         tc.GC = pc.G; tc.NC = pc.N; tc.NCHC = pc.G ? (M + pc.G - 1) / pc.G : 0;
         tc.GW = pw.G; tc.NW = pw.N; tc.NCHW = pw.G ? (M + pw.G - 1) / pw.G : 0;
         auto put = [&](std::vector<float>& img, size_t base, int rows, int n, int k, double v) {

@@ -17,7 +17,8 @@ struct TcPlan {
     int abufs = 0;   // A-operand (frame tile) buffers
     size_t smem = 0; // dynamic shared memory bytes
 };
-// rows_per_mixture = DP (whitening only) or 2*DP (whitening + regression).
-TcPlan tc_plan(int M, int KP, int rows_per_mixture);
+// rows_per_mixture = DP (whitening only) or 2*DP (whitening + regression); part_rows = floats per
+// frame of the epilogue groups' merge buffer.
+TcPlan tc_plan(int M, int KP, int rows_per_mixture, int part_rows);
 
 }  // namespace vcb
