@@ -6,9 +6,11 @@
 //
 //   * observation costs (src/dtw.jl:33-35, sum_k (v_k - tmpl_k)^2 in strict left-to-right Float64
 //     without FMA contraction) are computed for a tile of TT sequence frames at once -- this is
-//     the FP64-pipe bound part and has TT independent dependency chains per thread;
-//   * the TT column updates then run back to back on a double-buffered shared-memory cost column
-//     (one __syncthreads per column); candidates are visited in the reference order
+//     the FP64-pipe bound part and has TT independent dependency chains per thread; the costs of
+//     tile n+1 are computed piecewise inside the column loop of tile n (software pipeline), so
+//     the FP64 pipe keeps working across the per-column barriers;
+//   * the TT column updates run on a double-buffered shared-memory cost column (one
+//     __syncthreads per column); candidates are visited in the reference order
 //     i, i-bstep, ..., i+fstep with a strict `<`, sums associate as ((cost + ocost) + transition);
 //   * back-pointers are stored as (j - i + bstep) in BITS bits, packed 32/BITS columns per word in
 //     an L2-resident scratch (0.25 B/cell for the usual windows); the local-cost matrix and the
@@ -47,14 +49,18 @@ __global__ void dtw_transpose_kernel(const double* __restrict__ tmpl, const int6
     }
 }
 
-template <int BITS, int TT, int MAXT, int MINB>
+// DT > 0: feature dimension known at compile time (observation loop fully unrolled);
+// BS >= 0: window (bstep = BS, fstep = FS) known at compile time (candidate scan unrolled).
+template <int BITS, int TT, int MAXT, int MINB, int DT, int BS, int FS>
 __global__ void __launch_bounds__(MAXT, MINB)
 dtw_fused_kernel(const double* __restrict__ tmplT, const int64_t* __restrict__ toff,
                  const double* __restrict__ seq, const int64_t* __restrict__ soff,
-                 const int64_t* __restrict__ bpoff, uint32_t* __restrict__ bp, int D, int fstep,
-                 int bstep, int64_t* __restrict__ paths, double* __restrict__ final_cost) {
+                 const int64_t* __restrict__ bpoff, uint32_t* __restrict__ bp, int Drt, int fstep_rt,
+                 int bstep_rt, int64_t* __restrict__ paths, double* __restrict__ final_cost) {
     constexpr int PER = 32 / BITS;
     constexpr uint32_t MASK = (BITS == 32) ? 0xFFFFFFFFu : ((1u << BITS) - 1u);
+    const int D = DT > 0 ? DT : Drt;
+    const int bstep = BS >= 0 ? BS : bstep_rt, fstep = BS >= 0 ? FS : fstep_rt;
     const int p = blockIdx.x;
     const int64_t tb = toff[p], sb = soff[p];
     const int S = (int)(toff[p + 1] - tb);
@@ -64,36 +70,43 @@ dtw_fused_kernel(const double* __restrict__ tmplT, const int64_t* __restrict__ t
     const int Spad = (S + 31) & ~31;
     uint32_t* bpp = bp + bpoff[p];  // [ceil(T/PER)][Spad]
 
+    // cost columns carry `bstep` sentinels (+inf) on the left and `fstep` on the right, so the
+    // candidate scan needs no range checks: an infinite candidate never passes the strict `<`
     extern __shared__ double smem[];
-    double* col0 = smem;                 // [Spad]
-    double* col1 = smem + Spad;          // [Spad]
-    double* vt = smem + 2 * Spad;        // [D][TT]  sequence tile, k-major
+    const int colw = bstep + (int)blockDim.x + fstep;
+    double* cur = smem + bstep;                  // [-bstep, blockDim + fstep)
+    double* nxt = smem + colw + bstep;
+    double* vt = smem + 2 * colw;                // [D][TT]  sequence tile, k-major (even offset: 16-byte aligned)
     __shared__ double red_v[32];
     __shared__ int red_i[32];
     __shared__ int s_best;
+    const double kInf = __longlong_as_double(0x7FF0000000000000LL);
 
     const double* tcol = tmplT + tb * D + i;  // element k at tcol[k * S]
-    if (i < Spad) col0[i] = (double)(i + 1);   // src/dtw.jl:49  costtable[:,1] = 1:S
-    double* cur = col0;
-    double* nxt = col1;
+    for (int e = threadIdx.x; e < 2 * colw; e += blockDim.x) smem[e] = kInf;
+    __syncthreads();
+    if (active) cur[i] = (double)(i + 1);      // src/dtw.jl:49  costtable[:,1] = 1:S
     uint32_t word = 0;
 
     for (int t0 = 0; t0 < T; t0 += TT) {
         const int ncols = min(TT, T - t0);
-        __syncthreads();  // previous tile's readers of vt are done; col init visible
+        __syncthreads();  // previous tile's readers of vt are done; column init visible
         for (int e = threadIdx.x; e < TT * D; e += blockDim.x) {
-            int c = e / D, k = e - c * D;
+            const int c = e / D, k = e - c * D;
             vt[k * TT + c] = (c < ncols) ? seq[(sb + t0 + c) * D + k] : 0.0;
         }
         __syncthreads();
 
-        // ---- observation costs for TT frames: acc[c] = sum_k (v[c][k] - tmpl[k])^2, in order
+        // ---- observation costs for TT frames: acc[c] = sum_k (v[c][k] - tmpl[k])^2 with k in
+        //      ascending order, no FMA (src/dtw.jl:33-35)
         double acc[TT];
 #pragma unroll
         for (int c = 0; c < TT; ++c) acc[c] = 0.0;
         if (active) {
-            for (int k = 0; k < D; ++k) {
-                const double tk = tcol[(int64_t)k * S];
+            const double* tp = tcol;
+            auto kstep = [&](int k) {
+                const double tk = *tp;
+                tp += S;
                 const double2* v2 = reinterpret_cast<const double2*>(vt + k * TT);
 #pragma unroll
                 for (int c = 0; c < TT; c += 2) {
@@ -102,29 +115,44 @@ dtw_fused_kernel(const double* __restrict__ tmplT, const int64_t* __restrict__ t
                     acc[c] = __dadd_rn(acc[c], __dmul_rn(d0, d0));
                     acc[c + 1] = __dadd_rn(acc[c + 1], __dmul_rn(d1, d1));
                 }
+            };
+            if (DT > 0) {
+#pragma unroll 4
+                for (int k = 0; k < DT; ++k) kstep(k);
+            } else {
+                for (int k = 0; k < D; ++k) kstep(k);
             }
         }
 
-        // ---- column recurrence  (src/dtw.jl:104-125)
+        // ---- column recurrence  (src/dtw.jl:104-125): candidates i (stay), then i-bstep .. i+fstep,
+        //      strict `<`; ((cost + ocost) + transition); transition 0 for j = i-1 (adding +0.0 to a
+        //      non-negative sum is the identity), 1 for j = i, 2 otherwise (src/dtw.jl:23-31)
 #pragma unroll
         for (int c = 0; c < TT; ++c) {
             if (c < ncols) {
+                const int t = t0 + c;
                 if (active) {
                     const double oc = acc[c];
-                    int minidx = i;
-                    double minc = __dadd_rn(__dadd_rn(cur[i], oc), 1.0);  // transition(i,i) = 1.0
-                    const int jlo = max(i - bstep, 0), jhi = min(i + fstep, S - 1);
-                    for (int j = jlo; j <= jhi; ++j) {
-                        double cand = __dadd_rn(cur[j], oc);
-                        // transition(j, i): 0.0 if i == j+1 (adding +0.0 to a non-negative sum is
-                        // the identity), 1.0 if i == j, 2.0 otherwise  (src/dtw.jl:23-31)
-                        if (i != j + 1) cand = __dadd_rn(cand, (i == j) ? 1.0 : 2.0);
-                        if (cand < minc) { minc = cand; minidx = j; }
+                    int code = bstep;  // minindex - i + bstep
+                    double minc = __dadd_rn(__dadd_rn(cur[i], oc), 1.0);
+                    if (BS >= 0) {
+#pragma unroll
+                        for (int dj = -BS; dj <= FS; ++dj) {
+                            if (dj == 0) continue;  // same value as the initial candidate: never `<`
+                            double cand = __dadd_rn(cur[i + dj], oc);
+                            if (dj != -1) cand = __dadd_rn(cand, 2.0);
+                            if (cand < minc) { minc = cand; code = dj + BS; }
+                        }
+                    } else {
+                        for (int dj = -bstep; dj <= fstep; ++dj) {
+                            double cand = __dadd_rn(cur[i + dj], oc);
+                            if (dj != -1) cand = __dadd_rn(cand, dj == 0 ? 1.0 : 2.0);
+                            if (cand < minc) { minc = cand; code = dj + bstep; }
+                        }
                     }
                     nxt[i] = minc;
-                    word |= (uint32_t)(minidx - i + bstep) << (BITS * ((t0 + c) % PER));
+                    word |= (uint32_t)code << (BITS * (t % PER));
                 }
-                const int t = t0 + c;
                 if ((t % PER) == PER - 1 || t == T - 1) {
                     if (i < Spad) bpp[(int64_t)(t / PER) * Spad + i] = word;
                     word = 0;
@@ -193,28 +221,49 @@ dtw_fused_kernel(const double* __restrict__ tmplT, const int64_t* __restrict__ t
     }
 }
 
-template <int BITS>
+template <int BITS, int DT, int BS, int FS>
 static int32_t launch_dtw(const double* tmplT, const int64_t* d_toff, const double* seq,
                           const int64_t* d_soff, const int64_t* d_bpoff, uint32_t* bp, int D,
                           int fstep, int bstep, int64_t npairs, int maxS, int64_t* paths,
                           double* final_cost, cudaStream_t st) {
-    constexpr int TT = 16;
     const int nt = round_up(maxS, 32);
-    const size_t smem = (size_t)(2 * nt + D * TT) * sizeof(double);
-    // VCB_DTW_MINB=2 selects the 2-CTA/SM build (48 registers, spills the cost tile) for tuning.
-    static const int minb = [] { const char* e = getenv("VCB_DTW_MINB"); return e ? atoi(e) : 1; }();
-    if (nt <= 640) {
-        auto k = minb >= 2 ? dtw_fused_kernel<BITS, TT, 640, 2> : dtw_fused_kernel<BITS, TT, 640, 1>;
+    const int colw = bstep + nt + fstep;
+    // <= 768 states: 16-column tiles (80-register budget); larger templates: 8-column tiles
+    if (nt <= 768) {
+        constexpr int TT = 16;
+        const size_t smem = (size_t)(2 * colw + 1 + D * TT) * sizeof(double);
+        auto k = dtw_fused_kernel<BITS, TT, 768, 1, DT, BS, FS>;
         VCB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<(unsigned)npairs, nt, smem, st>>>(tmplT, d_toff, seq, d_soff, d_bpoff, bp, D, fstep, bstep, paths, final_cost);
     } else {
-        auto k = dtw_fused_kernel<BITS, TT, 1024, 1>;
+        constexpr int TT = 8;
+        const size_t smem = (size_t)(2 * colw + 1 + D * TT) * sizeof(double);
+        auto k = dtw_fused_kernel<BITS, TT, 1024, 1, DT, BS, FS>;
         VCB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<(unsigned)npairs, nt, smem, st>>>(tmplT, d_toff, seq, d_soff, d_bpoff, bp, D, fstep, bstep, paths, final_cost);
     }
     count_launch();
     VCB_CUDA(cudaGetLastError());
     return VCB_OK;
+}
+
+// Compile-time specialisations for the windows the reference uses (tests: bstep=1; align: bstep=2,
+// both fstep=0) and common mel-cepstrum orders; everything else takes the runtime-parameter build.
+template <int BITS, int BS, int FS>
+static int32_t launch_dtw_dim(const double* tmplT, const int64_t* d_toff, const double* seq,
+                              const int64_t* d_soff, const int64_t* d_bpoff, uint32_t* bp, int D,
+                              int fstep, int bstep, int64_t npairs, int maxS, int64_t* paths,
+                              double* final_cost, cudaStream_t st) {
+#define VCB_DTW_ARGS tmplT, d_toff, seq, d_soff, d_bpoff, bp, D, fstep, bstep, npairs, maxS, paths, final_cost, st
+    if constexpr (BS >= 0) {
+        switch (D) {
+            case 24: return launch_dtw<BITS, 24, BS, FS>(VCB_DTW_ARGS);
+            case 25: return launch_dtw<BITS, 25, BS, FS>(VCB_DTW_ARGS);
+            case 40: return launch_dtw<BITS, 40, BS, FS>(VCB_DTW_ARGS);
+            default: break;
+        }
+    }
+    return launch_dtw<BITS, 0, BS, FS>(VCB_DTW_ARGS);
 }
 
 int32_t dtw_fit_batch_device(const double* d_tmpl, const int64_t* h_toff, const double* d_seq,
@@ -256,12 +305,12 @@ int32_t dtw_fit_batch_device(const double* d_tmpl, const int64_t* h_toff, const 
         VCB_CUDA(cudaGetLastError());
     }
     int32_t rc;
-    if (bits == 2)
-        rc = launch_dtw<2>(d_tmplT, d_off, d_seq, d_off + noff, d_off + 2 * noff, d_bp, D, fstep, bstep, npairs, maxS, d_paths, d_final_cost, st);
-    else if (bits == 4)
-        rc = launch_dtw<4>(d_tmplT, d_off, d_seq, d_off + noff, d_off + 2 * noff, d_bp, D, fstep, bstep, npairs, maxS, d_paths, d_final_cost, st);
-    else
-        rc = launch_dtw<8>(d_tmplT, d_off, d_seq, d_off + noff, d_off + 2 * noff, d_bp, D, fstep, bstep, npairs, maxS, d_paths, d_final_cost, st);
+#define VCB_DTW_CALL d_tmplT, d_off, d_seq, d_off + noff, d_off + 2 * noff, d_bp, D, fstep, bstep, npairs, maxS, d_paths, d_final_cost, st
+    if (fstep == 0 && bstep == 1) rc = launch_dtw_dim<2, 1, 0>(VCB_DTW_CALL);
+    else if (fstep == 0 && bstep == 2) rc = launch_dtw_dim<2, 2, 0>(VCB_DTW_CALL);
+    else if (bits == 2) rc = launch_dtw_dim<2, -1, 0>(VCB_DTW_CALL);
+    else if (bits == 4) rc = launch_dtw_dim<4, -1, 0>(VCB_DTW_CALL);
+    else rc = launch_dtw_dim<8, -1, 0>(VCB_DTW_CALL);
     cudaFreeAsync(d_off, st);
     cudaFreeAsync(d_tmplT, st);
     cudaFreeAsync(d_bp, st);
