@@ -91,6 +91,7 @@ struct vcb_gmmmap {
     std::vector<double> xbar;  // centring vector (weighted mean of mux), applied in Float64
     // device Float64 (exact-path operands: arg-max re-check, E_t, posterior output)
     vcb::DevBuf<double> d_linv;  // [M][D][D] row-major inverse Cholesky factor (lower)
+    vcb::DevBuf<double> d_linv_cm;  // the same, column-major ([k][r]) for coalesced row-parallel reads
     vcb::DevBuf<double> d_mux, d_muy;  // [M][D]
     vcb::DevBuf<double> d_A;     // [M][D*D] column-major (A[i + k*D])
     vcb::DevBuf<double> d_c;     // [M]

@@ -38,14 +38,19 @@ __device__ __forceinline__ double loglik_fp64(const double* __restrict__ linv, c
 
 constexpr int kExactThreads = 128;
 
-__global__ void __launch_bounds__(kExactThreads)
+// Exact arg-max for the frames the fp32/tf32 kernels flagged as near ties.  One block per flagged
+// frame (grid-stride); warp w takes mixtures w, w+8, ...; lane = row r of z = Linv_m (x - mux_m),
+// read from the column-major copy of Linv so every k step is one coalesced load.
+constexpr int kRecheckThreads = 256;
+__global__ void __launch_bounds__(kRecheckThreads)
 recheck_argmax_kernel(const double* __restrict__ X, int64_t ldx, const int* __restrict__ flag_count,
-                      const int64_t* __restrict__ flag_list, const double* __restrict__ linv,
+                      const int64_t* __restrict__ flag_list, const double* __restrict__ linv_cm,
                       const double* __restrict__ mux, const double* __restrict__ c, int D, int M,
                       int32_t* __restrict__ mhat) {
     extern __shared__ double xs[];  // [D]
-    __shared__ double rv[kExactThreads / 32];
-    __shared__ int ri[kExactThreads / 32];
+    __shared__ double rv[kRecheckThreads / 32];
+    __shared__ int ri[kRecheckThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = kRecheckThreads / 32;
     const int n = *flag_count;
     for (int e = blockIdx.x; e < n; e += gridDim.x) {
         const int64_t t = flag_list[e];
@@ -54,20 +59,28 @@ recheck_argmax_kernel(const double* __restrict__ X, int64_t ldx, const int* __re
         __syncthreads();
         double bv = -INFINITY;
         int bi = 0x7FFFFFFF;
-        for (int m = threadIdx.x; m < M; m += blockDim.x) {
-            const double l = loglik_fp64(linv + (size_t)m * D * D, mux + (size_t)m * D, c[m], xs, D);
-            if (l > bv) { bv = l; bi = m; }  // ascending m per thread: first max kept
-        }
+        for (int m = warp; m < M; m += nwarps) {
+            const double* lm = linv_cm + (size_t)m * D * D;  // lm[k*D + r] = Linv[r][k]
+            const double* mu = mux + (size_t)m * D;
+            double q = 0.0;
+            for (int r0 = 0; r0 < D; r0 += 32) {
+                const int r = r0 + lane;
+                double z = 0.0;
+                if (r < D) {
+#pragma unroll 4
+                    for (int k = 0; k <= r0 + 31 && k < D; ++k) z = fma(lm[(size_t)k * D + r], xs[k] - mu[k], z);
+                }
+                q = fma(z, z, q);
+            }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_down_sync(0xFFFFFFFFu, bv, o);
-            const int oi = __shfl_down_sync(0xFFFFFFFFu, bi, o);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xFFFFFFFFu, q, o);
+            const double l = c[m] - 0.5 * q;
+            if (l > bv) { bv = l; bi = m; }  // ascending m per warp: first max kept
         }
-        if ((threadIdx.x & 31) == 0) { rv[threadIdx.x >> 5] = bv; ri[threadIdx.x >> 5] = bi; }
+        if (lane == 0) { rv[warp] = bv; ri[warp] = bi; }
         __syncthreads();
         if (threadIdx.x == 0) {
-            for (int w = 1; w < kExactThreads / 32; ++w)
+            for (int w = 1; w < nwarps; ++w)
                 if (rv[w] > bv || (rv[w] == bv && ri[w] < bi)) { bv = rv[w]; bi = ri[w]; }
             if (bi != 0x7FFFFFFF) mhat[t] = bi;
         }
@@ -135,8 +148,8 @@ int32_t simt_convert(const vcb_gmmmap& g, const double* dX, int64_t T, int64_t l
 
 int32_t recheck_argmax_fp64(const vcb_gmmmap& g, const double* dX, int64_t ldx, const int* d_flag_count,
                             const int64_t* d_flag_list, int32_t* d_mhat, cudaStream_t st) {
-    recheck_argmax_kernel<<<148 * 4, kExactThreads, g.D * sizeof(double), st>>>(
-        dX, ldx, d_flag_count, d_flag_list, g.d_linv.p, g.d_mux.p, g.d_c.p, g.D, g.M, d_mhat);
+    recheck_argmax_kernel<<<148 * 4, kRecheckThreads, g.D * sizeof(double), st>>>(
+        dX, ldx, d_flag_count, d_flag_list, g.d_linv_cm.p, g.d_mux.p, g.d_c.p, g.D, g.M, d_mhat);
     count_launch();
     VCB_CUDA(cudaGetLastError());
     return VCB_OK;

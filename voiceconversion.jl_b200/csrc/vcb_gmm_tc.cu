@@ -51,7 +51,8 @@ struct TcParams {
     int64_t ntiles;
     double* Y; int64_t ldy; int copy_power;
     int32_t* mhat; int* flag_count; int64_t* flag_list;
-    int debug;   // timing experiments only (VCB_TC_DEBUG): 1 = B loads shrunk to 16 B, 2 = MMAs skipped
+    int debug;   // timing experiments only (VCB_TC_DEBUG): 1 = B loads shrunk to 16 B, 2 = one k-step of MMAs,
+                 // 3 = both, 4 = epilogue does not read TMEM, 5 = A loaders skip the global loads
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -97,6 +98,15 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
+// One lane of a fully active warp (the issuing code stays warp-uniform so descriptors and
+// addresses live in uniform registers; a lane-0 branch instead makes the compiler wrap every
+// tcgen05.mma in an R2UR "waterfall" loop, ~60 extra cycles per instruction).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+    return pred != 0;
+}
+
 // D[tmem] (+)= A[smem] * B[smem], kind::tf32, single CTA
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -118,6 +128,42 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
                  : "r"(taddr));
     v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
     v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// NC consecutive columns (multiple of 8) with the fewest instructions: a tcgen05.ld costs ~45-60
+// cycles of issue per warp whatever its width (tools/micro/tmem_ld_bench.cu), so wide loads win.
+template <int NC>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
+    static_assert(NC % 8 == 0, "column count must be a multiple of 8");
+    if constexpr (NC >= 32) {
+        tmem_ld32(taddr, v);
+        if constexpr (NC > 32) tmem_ld_cols<NC - 32>(taddr + 32, v + 32);
+    } else if constexpr (NC >= 16) {
+        tmem_ld16(taddr, v);
+        if constexpr (NC > 16) tmem_ld_cols<NC - 16>(taddr + 16, v + 16);
+    } else if constexpr (NC == 8) {
+        tmem_ld8(taddr, v);
+    }
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -208,22 +254,25 @@ gmm_tc_kernel(const TcParams p) {
                 const uint32_t ph = (uint32_t)((it / S) & 1);
                 const int c = (int)(it % NCH);
                 mbar_wait(b_empty(s), ph ^ 1);
-                const uint32_t nbytes = (p.debug == 1) ? 16u : b_bytes;
+                const uint32_t nbytes = (p.debug == 1 || p.debug == 3) ? 16u : b_bytes;
                 mbar_expect_tx(b_full(s), nbytes);
                 bulk_g2s(smem_u32(b_smem + (size_t)s * b_bytes), p.B + (size_t)c * 2 * N * KP, nbytes, b_full(s));
             }
         }
     } else if (warp == kMmaWarp) {
-        // ======================= MMA issuer =======================
-        if (lane == 0) {
+        // ======================= MMA issuer (whole warp runs the loop; one elected lane issues) ===
+        {
+            const uint32_t tmem_u = __shfl_sync(0xFFFFFFFFu, tmem_base, 0);
             const uint32_t idesc = make_idesc_tf32(kTileM, N);
-            const int ksteps = KP / 8;
+            const int ksteps = (p.debug == 2 || p.debug == 3) ? 1 : KP / 8;
+            const uint32_t a_base = smem_u32(a_smem), b_base = smem_u32(b_smem);
+            const uint64_t astep = (2u * (kTileM * 16u)) >> 4, bstep = (2u * ((uint32_t)N * 16u)) >> 4;
             int64_t it = 0;
             for (int64_t tl = 0; tl < my_tiles; ++tl) {
                 const int ab = (int)(tl % AB);
                 const uint32_t aph = (uint32_t)((tl / AB) & 1);
                 mbar_wait(a_full(ab), aph);
-                const uint32_t a_hi = smem_u32(a_smem + (size_t)ab * a_bytes);
+                const uint32_t a_hi = a_base + (uint32_t)ab * a_bytes;
                 for (int c = 0; c < NCH; ++c, ++it) {
                     const int s = (int)(it % S);
                     const uint32_t ph = (uint32_t)((it / S) & 1);
@@ -233,28 +282,32 @@ gmm_tc_kernel(const TcParams p) {
                     mbar_wait(acc_empty(acc), accph ^ 1);
                     tc_fence_after();
                     // Descriptors differ from their k-step-0 value only in the start-address field
-                    // (low word), which advances by two 16-byte K slices per k-step.  Issuing is
-                    // the scarce resource here (one thread, ~70 cycles per tcgen05.mma), so the
-                    // loop body is nothing but three MMAs and four 32-bit adds.
-                    const uint32_t b_hi = smem_u32(b_smem + (size_t)s * b_bytes);
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
+                    // (low word), which advances by two 16-byte K slices per k-step.
+                    const uint32_t b_hi = b_base + (uint32_t)s * b_bytes;
+                    const uint32_t d_tmem = tmem_u + (uint32_t)(acc * N);
                     uint64_t dah = make_desc(a_hi, kTileM * 16u, 128u);
                     uint64_t dal = make_desc(a_hi + a_half, kTileM * 16u, 128u);
                     uint64_t dbh = make_desc(b_hi, (uint32_t)N * 16u, 128u);
                     uint64_t dbl = make_desc(b_hi + b_half, (uint32_t)N * 16u, 128u);
-                    const uint64_t astep = (2u * (kTileM * 16u)) >> 4, bstep = (2u * ((uint32_t)N * 16u)) >> 4;
-                    umma_tf32(d_tmem, dal, dbh, idesc, 0u);  // small terms first; first MMA overwrites
-                    umma_tf32(d_tmem, dah, dbl, idesc, 1u);
-                    umma_tf32(d_tmem, dah, dbh, idesc, 1u);
-                    for (int kk = 1; kk < (p.debug == 2 ? 0 : ksteps); ++kk) {
-                        dah += astep; dal += astep; dbh += bstep; dbl += bstep;
-                        umma_tf32(d_tmem, dal, dbh, idesc, 1u);
+                    if (elect_one()) {
+                        umma_tf32(d_tmem, dal, dbh, idesc, 0u);  // small terms first; first MMA overwrites
                         umma_tf32(d_tmem, dah, dbl, idesc, 1u);
                         umma_tf32(d_tmem, dah, dbh, idesc, 1u);
                     }
-                    umma_commit(b_empty(s));     // B stage may be refilled once these MMAs retire
-                    umma_commit(acc_full(acc));  // accumulator ready for the epilogue
-                    if (c == NCH - 1) umma_commit(a_empty(ab));
+                    for (int kk = 1; kk < ksteps; ++kk) {
+                        dah += astep; dal += astep; dbh += bstep; dbl += bstep;
+                        if (elect_one()) {
+                            umma_tf32(d_tmem, dal, dbh, idesc, 1u);
+                            umma_tf32(d_tmem, dah, dbl, idesc, 1u);
+                            umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+                        }
+                    }
+                    if (elect_one()) {
+                        umma_commit(b_empty(s));     // B stage may be refilled once these MMAs retire
+                        umma_commit(acc_full(acc));  // accumulator ready for the epilogue
+                        if (c == NCH - 1) umma_commit(a_empty(ab));
+                    }
+                    __syncwarp();
                 }
             }
         }
@@ -283,7 +336,7 @@ gmm_tc_kernel(const TcParams p) {
                     for (int j = 0; j < 4; ++j) {
                         const int k = 4 * k4 + j;
                         double v = 0.0;
-                        if (live && k < p.D) v = x[k] - p.xbar[k];
+                        if (live && k < p.D && p.debug != 5) v = x[k] - p.xbar[k];
                         else if (k == p.D) v = 1.0;
                         const float fh = to_tf32((float)v);
                         hp[j] = fh;
@@ -321,14 +374,15 @@ gmm_tc_kernel(const TcParams p) {
                 mbar_wait(acc_full(acc), accph);
                 tc_fence_after();
                 const uint32_t tcol = tmem_base + lane_base + (uint32_t)(acc * N);
-                if (ROWS <= 64) {
+                if (p.debug == 4) {
+                    // timing experiment: accumulators are not read
+                } else if (ROWS <= 64) {
                     // Software pipeline over the mixtures of this chunk: the TMEM loads of mixture
                     // g+1 are in flight while mixture g is reduced (tcgen05.wait::ld waits for all
                     // outstanding loads, so the wait sits after the compute).
                     auto fetch = [&](float (&v)[LOADW], int g) {
                         const uint32_t mcol = tcol + (uint32_t)(g * ROWS);
-#pragma unroll
-                        for (int r = 0; r < ROWS; r += 8) tmem_ld8(mcol + r, v + r);
+                        tmem_ld_cols<LOADW>(mcol, v);
                     };
                     auto reduce = [&](const float (&v)[LOADW], int g) {
                         const int m = c * p.G + g;
@@ -383,9 +437,9 @@ gmm_tc_kernel(const TcParams p) {
 #pragma unroll
                         for (int r0 = 0; r0 < DP; r0 += 32) {
                             float v[32];
-#pragma unroll
-                            for (int r = 0; r < 32; r += 8)
-                                if (r0 + r < DP) tmem_ld8(mcol + r0 + r, v + r);
+                            constexpr int W0 = (DP >= 32) ? 32 : DP;
+                            if (r0 + 32 <= DP) tmem_ld_cols<W0>(mcol + r0, v);
+                            else tmem_ld_cols<(DP % 32) ? (DP % 32) : 32>(mcol + r0, v);
                             tmem_ld_wait();
 #pragma unroll
                             for (int r = 0; r < 32; ++r)
@@ -405,9 +459,9 @@ gmm_tc_kernel(const TcParams p) {
 #pragma unroll
                             for (int r0 = 0; r0 < DP; r0 += 32) {
                                 float v[32];
-#pragma unroll
-                                for (int r = 0; r < 32; r += 8)
-                                    if (r0 + r < DP) tmem_ld8(mcol + DP + r0 + r, v + r);
+                                constexpr int W0 = (DP >= 32) ? 32 : DP;
+                                if (r0 + 32 <= DP) tmem_ld_cols<W0>(mcol + DP + r0, v);
+                                else tmem_ld_cols<(DP % 32) ? (DP % 32) : 32>(mcol + DP + r0, v);
                                 tmem_ld_wait();
 #pragma unroll
                                 for (int r = 0; r < 32; ++r)
@@ -528,22 +582,27 @@ constexpr size_t kSmemLimit = 227 * 1024;
 }  // namespace
 
 TcPlan tc_plan(int M, int KP, int rows_per_mixture, int part_rows) {
+    // Pick (mixtures per chunk, A buffers) by estimated tensor-pipe time per tile.  Measured on
+    // B200 (tools/micro/umma_bench.cu): one thread issues a tcgen05.mma every ~84 cycles at best,
+    // an M=128 x N x K=8 tf32 MMA executes in ~N/2 + 11 cycles.
     TcPlan best;
     const size_t extra = kBarBytes + (size_t)part_rows * 128 * sizeof(float);
     const int gmax = 256 / rows_per_mixture;
     if (gmax < 1) return best;
-    // candidate groupings ordered by (padded mixture count, larger G first)
-    for (int abufs = 2; abufs >= 1 && best.G == 0; --abufs) {
-        int best_pad = 1 << 30;
+    const int ksteps = KP / 8;
+    double best_cost = 1e30;
+    for (int abufs = 2; abufs >= 1; --abufs) {
         for (int g = gmax; g >= 1; --g) {
             const int n = g * rows_per_mixture;
             if (n % 16) continue;
             const size_t a = (size_t)abufs * 2 * kTileM * KP * 4;
             const size_t bst = (size_t)2 * n * KP * 4;
             if (a + 2 * bst + extra > kSmemLimit) continue;
-            const int padded = (M + g - 1) / g * g;
-            if (padded < best_pad) {
-                best_pad = padded;
+            const int nch = (M + g - 1) / g;
+            const double per_mma = std::max(84.0, n / 2.0 + 11.0);
+            const double cost = (double)nch * ksteps * 3 * per_mma + (abufs == 1 ? 4000.0 : 0.0);
+            if (cost < best_cost - 1e-9) {
+                best_cost = cost;
                 int stages = (int)((kSmemLimit - extra - a) / bst);
                 if (stages > kMaxStages) stages = kMaxStages;
                 best.G = g; best.N = n; best.stages = stages; best.abufs = abufs;

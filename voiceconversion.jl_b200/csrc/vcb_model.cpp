@@ -195,7 +195,11 @@ int32_t build_gmmmap(const double* weights, const double* mu, const double* sigm
     }
 
     // ---- device uploads: Float64 exact-path operands
-    if (g.d_linv.upload(linv_all) != cudaSuccess || g.d_mux.upload(g.mux) != cudaSuccess ||
+    std::vector<double> linv_cm(DD * M);
+    for (int mm = 0; mm < M; ++mm)
+        for (int r = 0; r < D; ++r)
+            for (int k = 0; k < D; ++k) linv_cm[mm * DD + (size_t)k * D + r] = linv_all[mm * DD + (size_t)r * D + k];
+    if (g.d_linv.upload(linv_all) != cudaSuccess || g.d_linv_cm.upload(linv_cm) != cudaSuccess || g.d_mux.upload(g.mux) != cudaSuccess ||
         g.d_muy.upload(g.muy) != cudaSuccess || g.d_A.upload(g.A) != cudaSuccess ||
         g.d_c.upload(cst) != cudaSuccess || g.d_xbar.upload(g.xbar) != cudaSuccess)
         return fail(VCB_ECUDA, "model upload failed: %s", cudaGetErrorString(cudaGetLastError()));

@@ -33,36 +33,49 @@ namespace {
 __global__ void traj_e_kernel(const double* __restrict__ X, int64_t ldx, int64_t total,
                               const int32_t* __restrict__ mhat, const double* __restrict__ A,
                               const double* __restrict__ mux, const double* __restrict__ muy,
-                              const double* __restrict__ P, int D2, double* __restrict__ E,
+                              const double* __restrict__ P, int D2, int groups, double* __restrict__ E,
                               double* __restrict__ Gv, double* __restrict__ Eout) {
     extern __shared__ double sm[];  // per frame: dx[D2], e[D2]
-    const int tpf = blockDim.x;     // threads per frame (>= D2)
     const int f = threadIdx.y;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.y + f;
     double* dx = sm + (size_t)f * 2 * D2;
     double* ev = dx + D2;
-    const bool live = t < total;
-    const int m = live ? mhat[t] : 0;
     const int i = threadIdx.x;
-    if (live && i < D2) dx[i] = X[t * ldx + i] - mux[(size_t)m * D2 + i];
-    __syncthreads();
-    if (live && i < D2) {
-        const double* a = A + (size_t)m * D2 * D2 + i;  // A[i + k*D2]
-        double s = 0.0;
-        for (int k = 0; k < D2; ++k) s = fma(a[(size_t)k * D2], dx[k], s);
-        s += muy[(size_t)m * D2 + i];
-        ev[i] = s;
-        E[t * D2 + i] = s;
-        if (Eout) Eout[t * D2 + i] = s;
+    // a block walks `groups` consecutive groups of blockDim.y frames: neighbouring frames mostly
+    // share their mixture, so A_m and P_m are re-read from L1 instead of L2
+    for (int gi = 0; gi < groups; ++gi) {
+        const int64_t t = ((int64_t)blockIdx.x * groups + gi) * blockDim.y + f;
+        const bool live = t < total;
+        const int m = live ? mhat[t] : 0;
+        __syncthreads();
+        if (live && i < D2) dx[i] = X[t * ldx + i] - mux[(size_t)m * D2 + i];
+        __syncthreads();
+        if (live && i < D2) {
+            const double* a = A + (size_t)m * D2 * D2 + i;  // A[i + k*D2]
+            double s0 = 0.0, s1 = 0.0;
+            int k = 0;
+            for (; k + 1 < D2; k += 2) {
+                s0 = fma(a[(size_t)k * D2], dx[k], s0);
+                s1 = fma(a[(size_t)(k + 1) * D2], dx[k + 1], s1);
+            }
+            if (k < D2) s0 = fma(a[(size_t)k * D2], dx[k], s0);
+            const double s = (s0 + s1) + muy[(size_t)m * D2 + i];
+            ev[i] = s;
+            E[t * D2 + i] = s;
+            if (Eout) Eout[t * D2 + i] = s;
+        }
+        __syncthreads();
+        if (live && i < D2) {
+            const double* pm = P + (size_t)m * D2 * D2 + i;  // symmetric: row i == column i
+            double s0 = 0.0, s1 = 0.0;
+            int k = 0;
+            for (; k + 1 < D2; k += 2) {
+                s0 = fma(pm[(size_t)k * D2], ev[k], s0);
+                s1 = fma(pm[(size_t)(k + 1) * D2], ev[k + 1], s1);
+            }
+            if (k < D2) s0 = fma(pm[(size_t)k * D2], ev[k], s0);
+            Gv[t * D2 + i] = s0 + s1;
+        }
     }
-    __syncthreads();
-    if (live && i < D2) {
-        const double* pm = P + (size_t)m * D2 * D2 + i;  // symmetric: row i == column i
-        double s = 0.0;
-        for (int k = 0; k < D2; ++k) s = fma(pm[(size_t)k * D2], ev[k], s);
-        Gv[t * D2 + i] = s;
-    }
-    (void)tpf;
 }
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -480,9 +493,11 @@ int32_t traj_solve_device(const vcb_traj& tr, const double* dX, int64_t ldx, con
     VCB_CUDA(cudaMemsetAsync(derr, 0, sizeof(int), st));
     {
         const int tpf = round_up(D2, 32), fpb = std::max(1, 256 / tpf);
-        dim3 block(tpf, fpb), grid((unsigned)((total + fpb - 1) / fpb));
+        const int groups = 1;   // more groups trade parallelism for L1 reuse of A_m / P_m; 1 measured fastest on B200
+        const int64_t per_block = (int64_t)fpb * groups;
+        dim3 block(tpf, fpb), grid((unsigned)((total + per_block - 1) / per_block));
         traj_e_kernel<<<grid, block, (size_t)fpb * 2 * D2 * sizeof(double), st>>>(
-            dX, ldx, total, d_mhat, g.d_A.p, g.d_mux.p, g.d_muy.p, tr.d_P.p, D2, dE, dG, dEy_out);
+            dX, ldx, total, d_mhat, g.d_A.p, g.d_mux.p, g.d_muy.p, tr.d_P.p, D2, groups, dE, dG, dEy_out);
         count_launch();
         VCB_CUDA(cudaGetLastError());
     }
