@@ -71,7 +71,9 @@ struct DevBuf {
 
 // Packed operands of the tcgen05 (3xTF32) posterior + conditional-mean kernel, see vcb_fbf_tc.cu.
 struct vcb_tc_pack {
-    int KP = 0;             // padded reduction length (multiple of 8): [xc (D) | 1 | 0-pad]
+    int KP = 0;             // reduction length (multiple of 8): [xc (D) | 0-pad | ones (2)], see vcb_model.cpp
+    int c1 = 0;             // column of the first "ones" entry (the second is c1 + 1)
+    int koff = 0;           // 1 if the ones columns live in an extra, single-pass k-step
     int GC = 0, GW = 0;     // mixtures per MMA chunk: conversion kernel / whitening-only kernel
     int NC = 0, NW = 0;     // MMA N = GC*2*DP / GW*DP
     int NCHC = 0, NCHW = 0; // number of chunks = ceil(M / G)

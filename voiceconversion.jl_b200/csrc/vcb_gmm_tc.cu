@@ -3,24 +3,29 @@
 // Same mathematics as vcb_gmm_simt.cu (reference src/gmmmap.jl:101-118, src/gmm.jl:24-58), laid
 // out as one GEMM per 128-frame tile:
 //
-//     [128 frames x KP]  .  [KP x N]      KP = [xc (D) | 1 | 0-pad],  N = G mixtures x rows
-//        A = [xc | 1]          B = per mixture the rows of Linv_m (whitening, offset folded into
-//                                  the "1" column) and, for conversion, of [A_m | b_m]
+//     [128 frames x KP]  .  [KP x N]      KP = [xc (D) | 0-pad | 1 1],  N = G mixtures x rows
+//        A = [x - xbar | 1 1]   B = per mixture the rows of Linv_m (whitening) and, for conversion,
+//                                   of A_m (regression); the offsets o_m / b_m ride on the two
+//                                   "ones" columns as tf32 hi and lo parts
 //
 // so that TMEM receives z_m = Linv_m (x - mux_m) and Ey_m = muy_m + A_m (x - mux_m) for G mixtures
-// per MMA chunk.  fp32 accuracy is needed (real models have cond(Sxx) ~ 1e7; plain TF32 misses the
+// per MMA chunk.  When D is a multiple of 8 the ones columns form their own k-step, which needs a
+// single MMA (hi*hi is exact for them) instead of three: 10 instead of 12 MMAs per chunk at D = 24.  fp32 accuracy is needed (real models have cond(Sxx) ~ 1e7; plain TF32 misses the
 // 1e-4 parity bar by three orders of magnitude), so both operands are split into tf32 hi + lo
 // and each k-step issues three MMAs (hi.hi, hi.lo, lo.hi) into the same fp32 accumulator.
 //
-// Warp roles (one persistent CTA per SM, 256 threads):
-//   warps 0-3  epilogue: tcgen05.ld of their 32 TMEM lanes (one frame per thread), software-
-//              pipelined over the mixtures of a chunk, |z|^2 -> log-lik, online soft-max,
-//              posterior-weighted accumulation of Ey (conversion) or running top-2 (arg-max).
-//              Per-mixture means and log-likelihoods never leave the SM.  (The code also supports
-//              two groups, one per accumulator stage, merged through shared memory.)
-//   warp 4     B producer: cp.async.bulk (TMA 1-D) of pre-packed operand images, ring of stages.
-//   warp 5     MMA issuer: one lane issues tcgen05.mma / tcgen05.commit; owns the TMEM allocation.
-//   warps 6-7  A loaders (two frame rows per thread): read Float64 frames, centre in Float64, split to tf32 hi/lo, write the
+// Warp roles (one persistent CTA per SM, 384 threads, clusters of two CTAs):
+//   warps 0-7  two epilogue groups (0-3 / 4-7), each taking every other mixture of a chunk: tcgen05.ld of
+//              their 32 TMEM lanes (one frame per thread), software-pipelined over the mixtures of
+//              a chunk, |z|^2 -> log-lik, online soft-max, posterior-weighted accumulation of Ey
+//              (conversion) or running top-2 (arg-max); the two partial states of a tile merge
+//              through shared memory.  Per-mixture means and log-likelihoods never leave the SM.
+//   warp 8     B producer: cp.async.bulk (TMA 1-D) of pre-packed operand images into a ring of
+//              stages; each CTA of the cluster fetches half of every chunk from L2 and multicasts
+//              it to both (all CTAs stream the same operand, L2->SM traffic was the co-limiter).
+//   warp 9     MMA issuer: one elected lane issues tcgen05.mma / tcgen05.commit (the stage-free
+//              commit is multicast to both CTAs); owns the TMEM allocation.
+//   warps 10-11 A loaders (two frame rows per thread): read Float64 frames, centre in Float64, split to tf32 hi/lo, write the
 //              UMMA K-major (no-swizzle) image to shared memory, double-buffered across tiles.
 // Pipelines: smem B ring (full/empty), A double buffer (full/empty), TMEM accumulator double
 // buffer (full/empty) -- all mbarriers; tcgen05.commit signals the "empty"/"full" transitions.
@@ -33,10 +38,12 @@ namespace vcb {
 namespace {
 
 constexpr int kTileM = 128;
-// One epilogue group: TMEM can be read at only ~64 B/clk/SM (measured: two groups reading both
-// accumulator stages at once halve each other's rate and leave the MMA no free stage), so a single
-// group that keeps the read port busy while the MMA fills the other stage is the better schedule.
-constexpr int kEpiGroups = 1;
+// Two epilogue groups split the mixtures of every chunk between them.  An accumulator stage
+// cycles through MMA -> commit -> epilogue -> release, and with N = 192 only two stages fit in
+// TMEM, so the chunk rate is (t_mma + t_epilogue + hand-off latency) / 2: halving the epilogue's
+// per-chunk latency (a ~450-cycle dependent chain per mixture) is what raises it.  The groups'
+// partial soft-max states merge through shared memory at the end of a tile.
+constexpr int kEpiGroups = 2;
 constexpr int kProducerWarp = 4 * kEpiGroups, kMmaWarp = kProducerWarp + 1, kLoaderWarp0 = kProducerWarp + 2;
 constexpr int kThreads = (kLoaderWarp0 + 2) * 32;
 constexpr int kMaxStages = 4;
@@ -48,9 +55,12 @@ struct TcParams {
     const float* B;        // [NCH][2][N*KP] operand images (hi, lo)
     const float* cst;      // [NCH*G]
     int D, KP, G, NCH, N, stages, abufs;
+    int c1, koff;          // ones columns (c1, c1+1); koff = 1: they form a last k-step that needs one MMA
     int64_t ntiles;
     double* Y; int64_t ldy; int copy_power;
     int32_t* mhat; int* flag_count; int64_t* flag_list;
+    int cluster;  // CTAs per cluster sharing the B operand stream by TMA multicast (1 or 2)
+    long long* prof;   // VCB_TC_DEBUG=9: per-role wait/work cycle counters of CTA 0
     int debug;   // timing experiments only (VCB_TC_DEBUG): 1 = B loads shrunk to 16 B, 2 = one k-step of MMAs,
                  // 3 = both, 4 = epilogue does not read TMEM, 5 = A loaders skip the global loads
 };
@@ -80,6 +90,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "DONE:\n"
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
+// Polite wait for roles that are usually ahead of the pipeline (producer, loaders): back off between
+// polls so the spinning warp does not take issue slots from the epilogue warps on its scheduler.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(200);
+    }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -88,6 +113,21 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// The same copy delivered to the same shared-memory offset of every CTA in `mask`; each
+// destination CTA's mbarrier (same offset) receives the complete_tx.
+__device__ __forceinline__ void bulk_g2s_mcast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
@@ -119,6 +159,12 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
 // mbarrier arrives once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// arrive on the mbarrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
@@ -195,6 +241,19 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 // ---------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------
+#define TIMED_WAIT(bar, par, acc_var)                               \
+    do {                                                            \
+        const long long _t0 = clock64();                           \
+        mbar_wait(bar, par);                                        \
+        acc_var += clock64() - _t0;                                 \
+    } while (0)
+#define TIMED_WAIT_SLEEP(bar, par, acc_var)                         \
+    do {                                                            \
+        const long long _t0 = clock64();                           \
+        mbar_wait_sleep(bar, par);                                  \
+        acc_var += clock64() - _t0;                                 \
+    } while (0)
+
 template <int DP, bool CONVERT>
 __global__ void __launch_bounds__(kThreads, 1)
 gmm_tc_kernel(const TcParams p) {
@@ -224,15 +283,20 @@ gmm_tc_kernel(const TcParams p) {
     const uint32_t part_empty = bar0 + 8u * (9 + 2 * kMaxStages);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * kMaxStages);
     float* part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes);  // [PART_ROWS][128]
+    // column constants of the A operand: xbar[k] for data columns, -1 for the two ones columns, 0 for
+    // padding, so that every entry is x[k] - colc[k] without branches (x = 0 outside the data)
+    double* colc = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(bars) + 192);   // [KP] <= 104 doubles
+    for (int k = threadIdx.x; k < KP; k += blockDim.x)
+        colc[k] = (k < p.D) ? p.xbar[k] : ((k == p.c1 || k == p.c1 + 1) ? -1.0 : 0.0);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(a_full(i), 64);
             mbar_init(a_empty(i), 1);
             mbar_init(acc_full(i), 1);
-            mbar_init(acc_empty(i), 128);
+            mbar_init(acc_empty(i), 128 * kEpiGroups);
         }
-        for (int i = 0; i < kMaxStages; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
+        for (int i = 0; i < kMaxStages; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), (uint32_t)p.cluster); }
         mbar_init(part_full, 128);
         mbar_init(part_empty, 128);
         fence_barrier_init();
@@ -240,46 +304,64 @@ gmm_tc_kernel(const TcParams p) {
     if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), 512);
     tc_fence_before();
     __syncthreads();
+    if (p.cluster > 1) cluster_sync_all();   // peers' barriers are initialised before any remote arrive / multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int64_t my_tiles = (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    // every CTA runs the same number of tile iterations (tiles past the end are computed on zeros
+    // and not stored), so the CTAs of a cluster walk the shared B stream in lock step
+    const int64_t my_tiles = (p.ntiles + gridDim.x - 1) / gridDim.x;
+    const uint16_t cmask = (uint16_t)((1u << p.cluster) - 1u);
 
     if (warp == kProducerWarp) {
         // ======================= B producer =======================
         if (lane == 0) {
             const int64_t total = my_tiles * NCH;
+            long long w_prod = 0;
+            const long long t_begin = clock64();
             for (int64_t it = 0; it < total; ++it) {
                 const int s = (int)(it % S);
                 const uint32_t ph = (uint32_t)((it / S) & 1);
                 const int c = (int)(it % NCH);
-                mbar_wait(b_empty(s), ph ^ 1);
-                const uint32_t nbytes = (p.debug == 1 || p.debug == 3) ? 16u : b_bytes;
+                TIMED_WAIT_SLEEP(b_empty(s), ph ^ 1, w_prod);
+                const uint32_t nbytes = (p.debug == 1 || p.debug == 3) ? 32u : b_bytes;
                 mbar_expect_tx(b_full(s), nbytes);
-                bulk_g2s(smem_u32(b_smem + (size_t)s * b_bytes), p.B + (size_t)c * 2 * N * KP, nbytes, b_full(s));
+                const uint32_t dst = smem_u32(b_smem + (size_t)s * b_bytes);
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(p.B + (size_t)c * 2 * N * KP);
+                if (p.cluster > 1) {
+                    // each CTA fetches 1/cluster of the chunk from L2 and multicasts it to all
+                    const uint32_t slice = nbytes / (uint32_t)p.cluster;
+                    const uint32_t off = cluster_ctarank() * slice;
+                    bulk_g2s_mcast(dst + off, src + off, slice, b_full(s), cmask);
+                } else {
+                    bulk_g2s(dst, src, nbytes, b_full(s));
+                }
             }
+            if (p.prof && blockIdx.x == 0) { p.prof[0] = w_prod; p.prof[1] = clock64() - t_begin; }
         }
     } else if (warp == kMmaWarp) {
         // ======================= MMA issuer (whole warp runs the loop; one elected lane issues) ===
         {
             const uint32_t tmem_u = __shfl_sync(0xFFFFFFFFu, tmem_base, 0);
             const uint32_t idesc = make_idesc_tf32(kTileM, N);
-            const int ksteps = (p.debug == 2 || p.debug == 3) ? 1 : KP / 8;
+            const int ksteps = (p.debug == 2 || p.debug == 3) ? 1 : KP / 8 - p.koff;   // three-pass k-steps
             const uint32_t a_base = smem_u32(a_smem), b_base = smem_u32(b_smem);
             const uint64_t astep = (2u * (kTileM * 16u)) >> 4, bstep = (2u * ((uint32_t)N * 16u)) >> 4;
             int64_t it = 0;
+            long long w_a = 0, w_b = 0, w_acc = 0;
+            const long long t_begin = clock64();
             for (int64_t tl = 0; tl < my_tiles; ++tl) {
                 const int ab = (int)(tl % AB);
                 const uint32_t aph = (uint32_t)((tl / AB) & 1);
-                mbar_wait(a_full(ab), aph);
+                TIMED_WAIT(a_full(ab), aph, w_a);
                 const uint32_t a_hi = a_base + (uint32_t)ab * a_bytes;
                 for (int c = 0; c < NCH; ++c, ++it) {
                     const int s = (int)(it % S);
                     const uint32_t ph = (uint32_t)((it / S) & 1);
                     const int acc = (int)(it & 1);
                     const uint32_t accph = (uint32_t)((it >> 1) & 1);
-                    mbar_wait(b_full(s), ph);
-                    mbar_wait(acc_empty(acc), accph ^ 1);
+                    TIMED_WAIT(b_full(s), ph, w_b);
+                    TIMED_WAIT(acc_empty(acc), accph ^ 1, w_acc);
                     tc_fence_after();
                     // Descriptors differ from their k-step-0 value only in the start-address field
                     // (low word), which advances by two 16-byte K slices per k-step.
@@ -302,23 +384,32 @@ gmm_tc_kernel(const TcParams p) {
                             umma_tf32(d_tmem, dah, dbh, idesc, 1u);
                         }
                     }
+                    if (p.koff) {   // offset k-step: ones (exact in tf32) x [o_hi, o_lo]: one pass is exact
+                        dah += astep; dbh += bstep;
+                        if (elect_one()) umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+                    }
                     if (elect_one()) {
-                        umma_commit(b_empty(s));     // B stage may be refilled once these MMAs retire
+                        // B stage may be refilled once these MMAs retire -- in every CTA of the cluster
+                        if (p.cluster > 1) umma_commit_mcast(b_empty(s), cmask);
+                        else umma_commit(b_empty(s));
                         umma_commit(acc_full(acc));  // accumulator ready for the epilogue
                         if (c == NCH - 1) umma_commit(a_empty(ab));
                     }
                     __syncwarp();
                 }
             }
+            if (p.prof && blockIdx.x == 0 && lane == 0) { p.prof[2] = w_a; p.prof[3] = w_b; p.prof[4] = w_acc; p.prof[5] = clock64() - t_begin; }
         }
     } else if (warp >= kLoaderWarp0) {
         // ======================= A loaders (64 threads, two frame rows each) =======================
         const int row0 = threadIdx.x - kLoaderWarp0 * 32;
+        long long w_load = 0;
+        const long long t_begin = clock64();
         for (int64_t tl = 0; tl < my_tiles; ++tl) {
             const int ab = (int)(tl % AB);
             const uint32_t aph = (uint32_t)((tl / AB) & 1);
             const int64_t tile = blockIdx.x + tl * gridDim.x;
-            mbar_wait(a_empty(ab), aph ^ 1);
+            TIMED_WAIT_SLEEP(a_empty(ab), aph ^ 1, w_load);
             uint8_t* hi = a_smem + (size_t)ab * a_bytes;
             uint8_t* lo = hi + a_half;
 #pragma unroll
@@ -326,30 +417,41 @@ gmm_tc_kernel(const TcParams p) {
                 const int row = row0 + 64 * h;
                 const uint32_t row_off = (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
                 const int64_t t = tile * kTileM + row;
-                const bool live = t < p.T;
+                const bool live = t < p.T && p.debug != 5;
                 const double* x = p.X + (live ? t : 0) * p.ldx;
-                for (int k4 = 0; k4 < KP / 4; ++k4) {
-                    float4 hv, lv;
-                    float* hp = &hv.x;
-                    float* lp = &lv.x;
+                // all loads of (up to 32 columns of) the row are issued before any is used: the
+                // frames stream from HBM, so memory-level parallelism is what keeps this role off
+                // the critical path
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int k = 4 * k4 + j;
-                        double v = 0.0;
-                        if (live && k < p.D && p.debug != 5) v = x[k] - p.xbar[k];
-                        else if (k == p.D) v = 1.0;
-                        const float fh = to_tf32((float)v);
-                        hp[j] = fh;
-                        lp[j] = to_tf32((float)(v - (double)fh));
+                for (int k0 = 0; k0 < DP + 8; k0 += 32) {
+                    constexpr int CW = (DP + 8 < 32) ? DP + 8 : 32;
+                    double xv[CW];
+#pragma unroll
+                    for (int j = 0; j < CW; ++j) xv[j] = (live && k0 + j < p.D) ? x[k0 + j] : 0.0;
+#pragma unroll
+                    for (int j4 = 0; j4 < CW; j4 += 4) {
+                        if (k0 + j4 < KP) {
+                            float4 hv, lv;
+                            float* hp = &hv.x;
+                            float* lp = &lv.x;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const double v = xv[j4 + j] - colc[k0 + j4 + j];
+                                const float fh = to_tf32((float)v);
+                                hp[j] = fh;
+                                lp[j] = to_tf32((float)(v - (double)fh));
+                            }
+                            const uint32_t off = (uint32_t)((k0 + j4) >> 2) * (kTileM * 16u) + row_off;
+                            *reinterpret_cast<float4*>(hi + off) = hv;
+                            *reinterpret_cast<float4*>(lo + off) = lv;
+                        }
                     }
-                    const uint32_t off = (uint32_t)k4 * (kTileM * 16u) + row_off;
-                    *reinterpret_cast<float4*>(hi + off) = hv;
-                    *reinterpret_cast<float4*>(lo + off) = lv;
                 }
             }
             fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
             mbar_arrive(a_full(ab));
         }
+        if (p.prof && blockIdx.x == 0 && row0 == 0) { p.prof[12] = w_load; p.prof[13] = clock64() - t_begin; }
     } else {
         // ======================= epilogue (warps 0-7; thread = frame = TMEM lane) =======================
         const int group = warp >> 2;          // with two groups: the accumulator stage this group drains
@@ -357,6 +459,8 @@ gmm_tc_kernel(const TcParams p) {
         const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
         constexpr int LOADW = (ROWS <= 64) ? ROWS : 32;   // TMEM columns fetched per wait
         int64_t it = 0;
+        long long w_full = 0, w_part = 0;
+        const long long t_begin = clock64();
         for (int64_t tl = 0; tl < my_tiles; ++tl) {
             const int64_t tile = blockIdx.x + tl * gridDim.x;
             const int64_t t = tile * kTileM + row;
@@ -368,10 +472,9 @@ gmm_tc_kernel(const TcParams p) {
                 for (int r = 0; r < DP; ++r) y[r] = 0.f;
             }
             for (int c = 0; c < NCH; ++c, ++it) {
-                if (kEpiGroups == 2 && (int)(it & 1) != group) continue;
                 const int acc = (int)(it & 1);
                 const uint32_t accph = (uint32_t)((it >> 1) & 1);
-                mbar_wait(acc_full(acc), accph);
+                TIMED_WAIT(acc_full(acc), accph, w_full);
                 tc_fence_after();
                 const uint32_t tcol = tmem_base + lane_base + (uint32_t)(acc * N);
                 if (p.debug == 4) {
@@ -414,21 +517,21 @@ gmm_tc_kernel(const TcParams p) {
                             else if (l > second) second = l;
                         }
                     };
+                    // both groups drain the same chunk: group e takes mixtures e, e + kEpiGroups, ...
+                    // Two mixtures' columns are requested before either is reduced: with the MMA
+                    // of the other stage running, a TMEM load takes several hundred cycles, far
+                    // longer than reducing one mixture, so the loads must overlap each other.
+                    constexpr int GS = kEpiGroups;
                     float v0[LOADW], v1[LOADW];
-                    fetch(v0, 0);
-                    tmem_ld_wait();
-                    for (int g = 0; g < p.G; g += 2) {
-                        if (g + 1 < p.G) fetch(v1, g + 1);
-                        reduce(v0, g);
+                    for (int g = group; g < p.G; g += 2 * GS) {
+                        fetch(v0, g);
+                        if (g + GS < p.G) fetch(v1, g + GS);
                         tmem_ld_wait();
-                        if (g + 1 < p.G) {
-                            if (g + 2 < p.G) fetch(v0, g + 2);
-                            reduce(v1, g + 1);
-                            tmem_ld_wait();
-                        }
+                        reduce(v0, g);
+                        if (g + GS < p.G) reduce(v1, g + GS);
                     }
                 } else {
-                for (int g = 0; g < p.G; ++g) {
+                for (int g = group; g < p.G; g += kEpiGroups) {
                     const int m = c * p.G + g;
                     const uint32_t mcol = tcol + (uint32_t)(g * ROWS);
                     const float cm = p.cst[m];  // -inf for padding mixtures
@@ -479,7 +582,9 @@ gmm_tc_kernel(const TcParams p) {
             }
             // ---- merge the two groups' partial states of this tile (group 1 -> smem -> group 0)
             const uint32_t pph = (uint32_t)(tl & 1);
-            if (kEpiGroups == 2 && group == 1) {
+            // the merging/storing group alternates per tile so both groups carry the same load
+            const int merger = (kEpiGroups == 2) ? (int)(tl & 1) : 0;
+            if (kEpiGroups == 2 && group != merger) {
                 mbar_wait(part_empty, pph ^ 1);
                 part[0 * 128 + row] = mx;
                 if (CONVERT) {
@@ -493,7 +598,7 @@ gmm_tc_kernel(const TcParams p) {
                 }
                 mbar_arrive(part_full);
             } else {
-                if (kEpiGroups == 2) mbar_wait(part_full, pph);
+                if (kEpiGroups == 2) TIMED_WAIT(part_full, pph, w_part);
                 const float mxb = (kEpiGroups == 2) ? part[0 * 128 + row] : -INFINITY;
                 if (CONVERT) {
                     const float m2 = fmaxf(mx, mxb);
@@ -528,10 +633,15 @@ gmm_tc_kernel(const TcParams p) {
                 if (kEpiGroups == 2) mbar_arrive(part_empty);
             }
         }
+        if (p.prof && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 128)) {
+            const int o = threadIdx.x == 0 ? 6 : 9;
+            p.prof[o] = w_full; p.prof[o + 1] = w_part; p.prof[o + 2] = clock64() - t_begin;
+        }
     }
 
     tc_fence_before();
     __syncthreads();
+    if (p.cluster > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into it
     if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
@@ -539,14 +649,40 @@ gmm_tc_kernel(const TcParams p) {
 }
 
 template <int DP, bool CONVERT>
-int32_t launch_tc(const TcParams& p, size_t smem, cudaStream_t st) {
+int32_t launch_tc(const TcParams& p_in, size_t smem, cudaStream_t st) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    TcParams p = p_in;
     auto k = gmm_tc_kernel<DP, CONVERT>;
     VCB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)std::min<int64_t>(p.ntiles, sms);
-    k<<<grid, kThreads, smem, st>>>(p);
+    static const int want_cluster = [] { const char* e = getenv("VCB_TC_CLUSTER"); return e ? atoi(e) : 2; }();
+    // clusters of two share the B stream when there are at least two tiles per cluster to amortise it
+    p.cluster = (want_cluster >= 2 && p.ntiles >= 2 && (p.N * p.KP * 8) % 32 == 0) ? 2 : 1;
+    unsigned grid = (unsigned)std::min<int64_t>(p.ntiles, sms);
+    if (p.cluster == 2) grid &= ~1u;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)p.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    long long* d_prof = nullptr;
+    if (p.debug == 9) { cudaMalloc((void**)&d_prof, 16 * sizeof(long long)); cudaMemset(d_prof, 0, 16 * sizeof(long long)); p.prof = d_prof; }
+    VCB_CUDA(cudaLaunchKernelEx(&cfg, k, p));
+    if (d_prof) {
+        long long h[16];
+        cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
+        cudaFree(d_prof);
+        fprintf(stderr, "[tc prof CTA0] producer: wait b_empty %lld of %lld | mma: wait a_full %lld b_full %lld acc_empty %lld of %lld | epi0: wait acc_full %lld part %lld of %lld | epi1: wait acc_full %lld part %lld of %lld | loader: wait a_empty %lld of %lld\n",
+                h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11], h[12], h[13]);
+    }
     count_launch();
     VCB_CUDA(cudaGetLastError());
     return VCB_OK;
@@ -624,6 +760,7 @@ static void fill_common(const vcb_gmmmap& g, const double* dX, int64_t T, int64_
     p.X = dX; p.T = T; p.ldx = ldx; p.xbar = g.d_xbar.p;
     p.B = convert ? g.tc.Bc.p : g.tc.Bw.p;
     p.cst = g.tc.cst.p;
+    p.c1 = g.tc.c1; p.koff = g.tc.koff;
     p.D = g.D; p.KP = g.tc.KP; p.G = plan.G; p.N = plan.N;
     p.NCH = convert ? g.tc.NCHC : g.tc.NCHW;
     p.stages = plan.stages; p.abufs = plan.abufs;

@@ -230,7 +230,17 @@ int32_t build_gmmmap(const double* weights, const double* mu, const double* sigm
     {
         vcb_tc_pack& tc = g.tc;
         const int DP = g.DP;
-        tc.KP = round_up(D + 1, 8);
+        // K layout: [xc (D) | 0-pad to 8] with the offset carried by two "ones" columns (B holds
+        // the offset's tf32 hi part in the first and its lo part in the second, so ONE hi*hi MMA
+        // adds it at full precision).  The ones columns sit in the padding of the last data k-step
+        // when it has two spare columns, otherwise in an extra k-step that needs a single MMA
+        // instead of the three passes of a data k-step.
+        {
+            const int kdata = round_up(D, 8);
+            tc.c1 = (kdata - D >= 2) ? D : kdata;
+            tc.KP = (kdata - D >= 2) ? kdata : kdata + 8;
+            tc.koff = (kdata - D >= 2) ? 0 : 1;
+        }
         const TcPlan pc = tc_plan(M, tc.KP, 2 * DP, DP + 2), pw = tc_plan(M, tc.KP, DP, 4);
         tc.GC = pc.G; tc.NC = pc.N; tc.NCHC = pc.G ? (M + pc.G - 1) / pc.G : 0;
         tc.GW = pw.G; tc.NW = pw.N; tc.NCHW = pw.G ? (M + pw.G - 1) / pw.G : 0;
@@ -239,6 +249,12 @@ int32_t build_gmmmap(const double* weights, const double* mu, const double* sigm
             tf32_split(v, hi, lo);
             img[base + umma_kmajor_index(n, k, rows)] = hi;
             img[base + (size_t)rows * tc.KP + umma_kmajor_index(n, k, rows)] = lo;
+        };
+        auto put_off = [&](std::vector<float>& img, size_t base, int rows, int n, double v) {
+            float hi, lo;
+            tf32_split(v, hi, lo);
+            img[base + umma_kmajor_index(n, tc.c1, rows)] = hi;       // both parts in the hi image
+            img[base + umma_kmajor_index(n, tc.c1 + 1, rows)] = lo;
         };
         std::vector<float> bc((size_t)tc.NCHC * 2 * tc.NC * tc.KP, 0.0f);
         std::vector<float> bw((size_t)tc.NCHW * 2 * tc.NW * tc.KP, 0.0f);
@@ -256,8 +272,8 @@ int32_t build_gmmmap(const double* weights, const double* mu, const double* sigm
                         put(bc, base, tc.NC, nz, k, li[(size_t)r * D + k]);
                         put(bc, base, tc.NC, ne, k, g.A[m * DD + r + (size_t)k * D]);
                     }
-                    put(bc, base, tc.NC, nz, D, offw[(size_t)m * D + r]);
-                    put(bc, base, tc.NC, ne, D, offa[(size_t)m * D + r]);
+                    put_off(bc, base, tc.NC, nz, offw[(size_t)m * D + r]);
+                    put_off(bc, base, tc.NC, ne, offa[(size_t)m * D + r]);
                 }
             }
             if (tc.GW) {
@@ -266,7 +282,7 @@ int32_t build_gmmmap(const double* weights, const double* mu, const double* sigm
                 for (int r = 0; r < D; ++r) {
                     const int nz = gi * DP + r;
                     for (int k = 0; k < D; ++k) put(bw, base, tc.NW, nz, k, li[(size_t)r * D + k]);
-                    put(bw, base, tc.NW, nz, D, offw[(size_t)m * D + r]);
+                    put_off(bw, base, tc.NW, nz, offw[(size_t)m * D + r]);
                 }
             }
         }
