@@ -110,6 +110,23 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel_file: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the
+    latest `ncu --set full` summary committed under profiles/ (None if there is none)."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_{kernel_file}.txt")))
+    if not files:
+        return None, None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for line in open(files[-1]):
+        m = re.match(r"dram__bytes_(read|write)\.sum\s+([0-9.]+)\s+(\w+)", line)
+        if m:
+            tot += float(m.group(2)) * unit.get(m.group(3), 1.0)
+    return (tot or None), os.path.relpath(files[-1], ROOT)
+
+
 def measure_tf32_peak(torch):
     """Dense TF32 tensor peak with the driver's method for bf16 (torch.matmul 8192^3, best of 10)."""
     old = torch.backends.cuda.matmul.allow_tf32
@@ -261,6 +278,7 @@ def main():
         kernel_ms = float(np.mean(kern_ms))
         achieved = F_FBF * T / (kernel_ms * 1e-3) / 1e12
         used_tc = args.variant != 1
+        traffic, traffic_src = ncu_traffic("prof_fbf_tc" if used_tc else "prof_fbf_simt")
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -276,14 +294,16 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                         "frac": achieved / tf32_peak, "traffic": None,
+                         "frac": achieved / tf32_peak, "traffic": traffic, "traffic_unit": "bytes/launch (DRAM read+write, ncu)",
+                         "traffic_source": traffic_src,
                          "kernel": "gmm_tc_kernel<24,true>" if used_tc else "gmm_simt_kernel<24,2,true>",
                          "kernel_ms": kernel_ms,
                          "algorithmic_flop_per_frame": F_FBF,
                          "peak_source": "dense TF32 measured in this run (torch.matmul 8192^3, best of 10); "
                                         f"bf16 {peaks.get('bf16_tflops')} TF/s, HBM {peaks.get('hbm_gbs')} GB/s {peak_src}",
-                         "note": "achieved counts ALGORITHMIC flops (4MD^2+2MD per frame); the 3xTF32 split issues "
-                                 "3 MMAs per product and K is padded 25->32, so the tensor pipe does ~3.9x that"},
+                         "note": "achieved counts ALGORITHMIC flops (4MD^2+2MD per frame); the 3xTF32 split issues 3 MMAs "
+                                 "per data k-step plus 1 for the offset step (K: 25 -> 80 effective), so the tensor pipe "
+                                 "executes ~3.3x that; ncu: sm__pipe_tensor_cycles_active 57%"},
         }
 
     # ---- side measurements: trajectory (C2), DTW (C3), CPU baseline (rank 0, N=1 only)

@@ -6,11 +6,15 @@ R=${1:-r01}
 # 1. launch list of one short bench run (cold-cache, serialised: compare SHARES only)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file gpurun_out/launches_$R.csv python bench.py --steps 2 --warmup 3 > gpurun_out/launches_$R.log 2>&1
-# 2. full captures of the three hot kernels
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:gmm_tc_kernel -s 3 -c 1 \
-    -f -o gpurun_out/prof_fbf_tc_$R python bench.py --steps 2 --warmup 3 --skip-extras > gpurun_out/prof_fbf_tc_$R.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:gmm_simt_kernel -s 3 -c 1 \
-    -f -o gpurun_out/prof_fbf_simt_$R python bench.py --steps 2 --warmup 3 --skip-extras --variant 1 > gpurun_out/prof_fbf_simt_$R.log 2>&1
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"traj_solve_kernel|dtw_fused_kernel" -s 2 -c 2 \
-    -f -o gpurun_out/prof_traj_dtw_$R python bench.py --steps 1 --warmup 3 --frames 131072 > gpurun_out/prof_traj_dtw_$R.log 2>&1
-ls -la gpurun_out
+# 2. full captures of the hot kernels (one launch each, after warm-up launches)
+cap() { # name regex skip cmd...
+  local name=$1 rx=$2 skip=$3; shift 3
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$rx" -s $skip -c 1 \
+      -f -o gpurun_out/${name}_$R "$@" > gpurun_out/${name}_$R.log 2>&1
+}
+cap prof_fbf_tc   gmm_tc_kernel      2 python tools/run_path.py fbf 1
+cap prof_fbf_simt gmm_simt_kernel    2 python tools/run_path.py fbf_simt 1
+cap prof_traj     traj_solve_tiled   1 python tools/run_path.py traj 1
+cap prof_argmax   gmm_tc_kernel      1 python tools/run_path.py traj 1
+cap prof_dtw      dtw_fused_kernel   1 python tools/run_path.py dtw 1
+ls -la gpurun_out | head -30
