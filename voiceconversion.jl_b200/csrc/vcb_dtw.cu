@@ -229,7 +229,16 @@ static int32_t launch_dtw(const double* tmplT, const int64_t* d_toff, const doub
     const int nt = round_up(maxS, 32);
     const int colw = bstep + nt + fstep;
     // <= 768 states: 16-column tiles (80-register budget); larger templates: 8-column tiles
-    if (nt <= 768) {
+    static const int two_ctas = [] { const char* e = getenv("VCB_DTW_2CTA"); return e ? atoi(e) : 1; }();
+    if (nt <= 672 && two_ctas && DT > 0) {   // (the runtime-dimension build would spill at 48 registers)
+        // two CTAs per SM (8-column tiles, 48 registers): one CTA's barrier-paced recurrence overlaps
+        // the other's FP64-bound observation costs
+        constexpr int TT = 8;
+        const size_t smem = (size_t)(2 * colw + 1 + D * TT) * sizeof(double);
+        auto k = dtw_fused_kernel<BITS, TT, 672, 2, DT, BS, FS>;
+        VCB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<(unsigned)npairs, nt, smem, st>>>(tmplT, d_toff, seq, d_soff, d_bpoff, bp, D, fstep, bstep, paths, final_cost);
+    } else if (nt <= 768) {
         constexpr int TT = 16;
         const size_t smem = (size_t)(2 * colw + 1 + D * TT) * sizeof(double);
         auto k = dtw_fused_kernel<BITS, TT, 768, 1, DT, BS, FS>;

@@ -99,22 +99,22 @@ struct TrajParams {
     int* err;
 };
 
-// C (TS x TS register tile at rows i0.., cols j0..) (+)= sign * X * Y'   for k in [0, kmax),
-// X and Y stored column-major in shared memory: XT[k*LD + i] = X[i][k].
-template <int TS, int LD, bool SUB>
-__device__ __forceinline__ void tile_xyt(double (&c)[TS][TS], const double* __restrict__ XT,
-                                         const double* __restrict__ YT, int i0, int j0, int kmax) {
+// FP64 tensor-core tile product (mma.sync m8n8k4): acc (8x8 tile at rows 8*i8, cols 8*j8) +=
+// sum_{k < kmax} X[i][k] * Y[j][k], X and Y column-major in shared memory (XT[k*LD + i] = X[i][k]).
+// Fragment layout: A a0 = X[8*i8 + lane/4][k + lane%4], B b0 = Y[8*j8 + lane/4][k + lane%4],
+// C c0,c1 = [8*i8 + lane/4][8*j8 + 2*(lane%4) + {0,1}].  One warp instruction performs 256 FMAs,
+// so the block products cost ~8x fewer issue slots than per-thread DFMA tiles.
+__device__ __forceinline__ void dmma_tile(double& c0, double& c1, const double* __restrict__ XT,
+                                          const double* __restrict__ YT, int i8, int j8, int kmax,
+                                          int LD, int lane) {
+    const int r = lane >> 2, q = lane & 3;
+    const double* xa = XT + q * LD + i8 * 8 + r;
+    const double* yb = YT + q * LD + j8 * 8 + r;
 #pragma unroll 2
-    for (int k = 0; k < kmax; ++k) {
-        double a[TS], b[TS];
-#pragma unroll
-        for (int x = 0; x < TS; ++x) a[x] = XT[k * LD + i0 + x];
-#pragma unroll
-        for (int y = 0; y < TS; ++y) b[y] = YT[k * LD + j0 + y];
-#pragma unroll
-        for (int x = 0; x < TS; ++x)
-#pragma unroll
-            for (int y = 0; y < TS; ++y) c[x][y] = SUB ? fma(-a[x], b[y], c[x][y]) : fma(a[x], b[y], c[x][y]);
+    for (int k = 0; k < kmax; k += 4) {
+        const double a = xa[k * LD], b = yb[k * LD];
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
     }
 }
 
@@ -130,6 +130,7 @@ traj_solve_tiled(const TrajParams p) {
     const int Ds = p.Ds, D2 = 2 * Ds, BB = Ds * Ds;
     const int tid = threadIdx.x;
     const int ti = tid & 7, tj = tid >> 3, i0 = ti * TS, j0 = tj * TS;
+    const int lane = tid & 31, warp = tid >> 5;
     const int64_t c0 = p.chunk_off[blockIdx.x];
     const int T = (int)(p.chunk_off[blockIdx.x + 1] - c0);
     if (T <= 0) return;
@@ -212,37 +213,60 @@ traj_solve_tiled(const TrajParams p) {
             rv[tid] = r;
         }
         __syncthreads();
-        const int ktri = min(j0 + TS, DSP);  // Linv is lower triangular: Linv[j][k] = 0 for k > j
-        // ---- 1. G2 = L[t][t-2] = R[t][t-2] * Linv_{t-2}'
-        {
-            double c[TS][TS] = {};
-            if (t >= 2) tile_xyt<TS, LD, false>(c, W, Lm2inv, i0, j0, ktri);
-#pragma unroll
-            for (int y = 0; y < TS; ++y)
-#pragma unroll
-                for (int x = 0; x < TS; ++x) G2[(j0 + y) * LD + i0 + x] = c[x][y];
+        // Block products on the FP64 tensor cores: the TS x TS output tiles (8 x 8 each) are dealt
+        // to the two warps; fragment element (row, col pair) of this lane inside a tile:
+        const int fr = lane >> 2, fc = 2 * (lane & 3);
+        // ---- 1. G2 = L[t][t-2] = R[t][t-2] * Linv_{t-2}'   (Linv lower triangular: k < 8*(j8+1))
+        for (int tau = warp; tau < TS * TS; tau += 2) {
+            const int i8 = tau / TS, j8 = tau - i8 * TS;
+            double c0 = 0.0, c1 = 0.0;
+            if (t >= 2) dmma_tile(c0, c1, W, Lm2inv, i8, j8, 8 * (j8 + 1), LD, lane);
+            G2[(8 * j8 + fc) * LD + 8 * i8 + fr] = c0;
+            G2[(8 * j8 + fc + 1) * LD + 8 * i8 + fr] = c1;
         }
         __syncthreads();
         // ---- 2. Tm = R[t][t-1] - G2 * L[t-1][t-2]'  (into the W buffer; R[t][t-2] is dead)
-        if (t >= 2) tile_xyt<TS, LD, true>(r1, G2, Lt1t2, i0, j0, DSP);
 #pragma unroll
         for (int y = 0; y < TS; ++y)
 #pragma unroll
             for (int x = 0; x < TS; ++x) W[(j0 + y) * LD + i0 + x] = r1[x][y];
         __syncthreads();
+        if (t >= 2) {
+            for (int tau = warp; tau < TS * TS; tau += 2) {
+                const int i8 = tau / TS, j8 = tau - i8 * TS;
+                double c0 = 0.0, c1 = 0.0;
+                dmma_tile(c0, c1, G2, Lt1t2, i8, j8, DSP, LD, lane);
+                W[(8 * j8 + fc) * LD + 8 * i8 + fr] -= c0;
+                W[(8 * j8 + fc + 1) * LD + 8 * i8 + fr] -= c1;
+            }
+        }
+        __syncthreads();
         // ---- 3. G1 = L[t][t-1] = Tm * Linv_{t-1}'
-        {
-            double c[TS][TS] = {};
-            if (t >= 1) tile_xyt<TS, LD, false>(c, W, Lm1inv, i0, j0, ktri);
+        for (int tau = warp; tau < TS * TS; tau += 2) {
+            const int i8 = tau / TS, j8 = tau - i8 * TS;
+            double c0 = 0.0, c1 = 0.0;
+            if (t >= 1) dmma_tile(c0, c1, W, Lm1inv, i8, j8, 8 * (j8 + 1), LD, lane);
+            G1[(8 * j8 + fc) * LD + 8 * i8 + fr] = c0;
+            G1[(8 * j8 + fc + 1) * LD + 8 * i8 + fr] = c1;
+        }
+        __syncthreads();
+        // ---- 4. S = R[t][t] - G2 G2' - G1 G1'  (products into the W buffer -- Tm is dead -- then
+        //         every thread subtracts its own register tile)
+        if (t >= 1) {
+            for (int tau = warp; tau < TS * TS; tau += 2) {
+                const int i8 = tau / TS, j8 = tau - i8 * TS;
+                double c0 = 0.0, c1 = 0.0;
+                dmma_tile(c0, c1, G1, G1, i8, j8, DSP, LD, lane);
+                if (t >= 2) dmma_tile(c0, c1, G2, G2, i8, j8, DSP, LD, lane);
+                W[(8 * j8 + fc) * LD + 8 * i8 + fr] = c0;
+                W[(8 * j8 + fc + 1) * LD + 8 * i8 + fr] = c1;
+            }
+            __syncthreads();
 #pragma unroll
             for (int y = 0; y < TS; ++y)
 #pragma unroll
-                for (int x = 0; x < TS; ++x) G1[(j0 + y) * LD + i0 + x] = c[x][y];
+                for (int x = 0; x < TS; ++x) s[x][y] -= W[(j0 + y) * LD + i0 + x];
         }
-        __syncthreads();
-        // ---- 4. S = R[t][t] - G2 G2' - G1 G1'
-        if (t >= 2) tile_xyt<TS, LD, true>(s, G2, G2, i0, j0, DSP);
-        if (t >= 1) tile_xyt<TS, LD, true>(s, G1, G1, i0, j0, DSP);
         // ---- 5. blocked right-looking Cholesky of S fused with W <- L^-1.  S and W tiles stay in
         //         registers; per block column: the diagonal tile is factorised and inverted by its
         //         owner, the panel and the matching rows of L^-1 are formed with that inverse and
