@@ -23,6 +23,7 @@
 #include <cstdlib>
 
 #include "vcb_kernels.h"
+#include "vcb_traj.h"
 
 namespace vcb {
 
@@ -86,18 +87,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-struct TrajParams {
-    const double* P;        // [M][D2*D2] symmetric precision blocks
-    const int32_t* mhat;    // [total] 0-based
-    const double* Gv;       // [total][D2]  g_t = P_t E_t
-    const int64_t* chunk_off;
-    double* Lst;            // [total][3][Ds*Ds]  Linv_tt, L[t][t-1], L[t][t-2], row-major, compact
-    double* Z;              // [total][Ds]
-    double* Y; int64_t ldy;
-    const double* Xpow; int64_t ldx; int copy_power;
-    int Ds;
-    int* err;
-};
 
 // FP64 tensor-core tile product (mma.sync m8n8k4): acc (8x8 tile at rows 8*i8, cols 8*j8) +=
 // sum_{k < kmax} X[i][k] * Y[j][k], X and Y column-major in shared memory (XT[k*LD + i] = X[i][k]).
@@ -511,7 +500,11 @@ int32_t traj_solve_device(const vcb_traj& tr, const double* dX, int64_t ldx, con
     int* derr = nullptr;
     VCB_CUDA(cudaMallocAsync((void**)&dE, (size_t)total * D2 * sizeof(double), st));
     VCB_CUDA(cudaMallocAsync((void**)&dG, (size_t)total * D2 * sizeof(double), st));
-    VCB_CUDA(cudaMallocAsync((void**)&dL, (size_t)total * 3 * BB * sizeof(double), st));
+    // VCB_TRAJ_SOLVER=tiled keeps the 64-thread CTA solver for dimensions the warp solver covers
+    static const bool force_tiled = [] { const char* e = getenv("VCB_TRAJ_SOLVER"); return e && e[0] == 't'; }();
+    const size_t warp_bytes = force_tiled ? 0 : traj_warp_factor_bytes(Ds);
+    const size_t factor_bytes = std::max((size_t)3 * BB * sizeof(double), warp_bytes);
+    VCB_CUDA(cudaMallocAsync((void**)&dL, (size_t)total * factor_bytes, st));
     VCB_CUDA(cudaMallocAsync((void**)&dZ, (size_t)total * Ds * sizeof(double), st));
     VCB_CUDA(cudaMallocAsync((void**)&derr, sizeof(int), st));
     VCB_CUDA(cudaMemsetAsync(derr, 0, sizeof(int), st));
@@ -531,7 +524,8 @@ int32_t traj_solve_device(const vcb_traj& tr, const double* dX, int64_t ldx, con
         p.P = tr.d_P.p; p.mhat = d_mhat; p.Gv = dG; p.chunk_off = d_chunk_off; p.Lst = dL; p.Z = dZ;
         p.Y = dY; p.ldy = ldy; p.Xpow = dX; p.ldx = ldx; p.copy_power = copy_power ? 1 : 0;
         p.Ds = Ds; p.err = derr;
-        switch ((Ds + 7) / 8) {
+        if (warp_bytes) rc = traj_warp_launch(p, nchunks, st);
+        else switch ((Ds + 7) / 8) {
             case 1: rc = launch_tiled<1>(p, nchunks, st); break;
             case 2: rc = launch_tiled<2>(p, nchunks, st); break;
             case 3: rc = launch_tiled<3>(p, nchunks, st); break;

@@ -1,0 +1,480 @@
+// vcb_traj_warp.cu -- K3w: trajectory ML solve, one WARP per chunk, blocks kept as FP64
+// tensor-core fragments (Ds <= 24).
+//
+// Same algorithm as vcb_traj.cu (block Cholesky of the block-pentadiagonal normal matrix
+// R = W' D^-1 W of reference src/trajectory_gmmmap.jl:95-105, sequential in time), laid out for
+// mma.sync.m8n8k4.f64:
+//   * every Ds x Ds block is NT x NT tiles of 8 x 8 (Ds <= 8 NT, padding carries a unit diagonal);
+//     a tile lives in the accumulator layout of the instruction: lane (r = lane/4, q = lane%4)
+//     holds X[r][2q], X[r][2q+1];
+//   * all block products of the factorisation have the form X * Y' (G2 = R2 Linv2', Tm = R1 - G2 Lp',
+//     G1 = Tm Linv1', S = R0 - G2 G2' - G1 G1', the Cholesky panel / trailing updates and the
+//     recursion for L^-1).  Because the contraction index may be visited in any order, two
+//     accumulator-layout tiles feed one product directly: DMMA #1 contracts the even columns
+//     (a = x.x, b = y.x), DMMA #2 the odd ones -- no shuffles, no shared-memory round trip;
+//   * the 8 x 8 diagonal tiles are factorised redundantly by every lane from a shared-memory copy
+//     (a warp has no cheaper way through that serial chain) and each lane back-substitutes the row
+//     of the inverse it owns;
+//   * no __syncthreads anywhere: a CTA is one warp, so chunks never wait for each other.
+// Per frame the kernel issues ~240 DMMA (61 k FP64 FMA) -- the FP64 pipe is the roofline -- and
+// streams 24 tiles (12 KB at NT = 3) of factors to HBM for the back substitution, which re-reads
+// them once in fragment order (each lane reads exactly the bytes it wrote).
+#include "vcb_kernels.h"
+#include "vcb_traj.h"
+
+namespace vcb {
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ void mma2(double2& c, const double2 x, const double2 y) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c.x), "+d"(c.y) : "d"(x.x), "d"(y.x));
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c.x), "+d"(c.y) : "d"(x.y), "d"(y.y));
+}
+__device__ __forceinline__ double2 neg2(const double2 v) { return make_double2(-v.x, -v.y); }
+__device__ __forceinline__ double2 zero2() { return make_double2(0.0, 0.0); }
+
+// transpose of an 8 x 8 tile in accumulator layout
+__device__ __forceinline__ double2 tile_transpose(const double2 x, int r, int q) {
+    const int s0 = (8 * q) | (r >> 1), s1 = (8 * q + 4) | (r >> 1);
+    const double a0 = __shfl_sync(kFull, x.x, s0), a1 = __shfl_sync(kFull, x.y, s0);
+    const double b0 = __shfl_sync(kFull, x.x, s1), b1 = __shfl_sync(kFull, x.y, s1);
+    return (r & 1) ? make_double2(a1, b1) : make_double2(a0, b0);
+}
+
+// Cholesky of the symmetric 8 x 8 tile d (lower triangle used) and the inverse of its factor,
+// returned in accumulator layout.  Every lane factorises the whole tile, then solves
+// L' y = e_r for row r of L^-1.
+__device__ __forceinline__ double2 diag_inverse(const double2 d, double* sd, int r, int q, int* err) {
+    __syncwarp();
+    *reinterpret_cast<double2*>(sd + r * 8 + 2 * q) = d;
+    __syncwarp();
+    double a[8][8], di[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c <= i; c += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(sd + i * 8 + c);
+            a[i][c] = v.x;
+            if (c + 1 <= i) a[i][c + 1] = v.y;
+        }
+    bool bad = false;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const double dd = a[c][c];
+        bad |= !(dd > 0.0);
+        di[c] = rsqrt(dd);
+#pragma unroll
+        for (int i = c + 1; i < 8; ++i) a[i][c] *= di[c];
+#pragma unroll
+        for (int i = c + 1; i < 8; ++i)
+#pragma unroll
+            for (int c2 = c + 1; c2 <= i; ++c2) a[i][c2] = fma(-a[i][c], a[c2][c], a[i][c2]);
+    }
+    if (bad) atomicExch(err, 1);
+    double y[8];
+#pragma unroll
+    for (int k = 7; k >= 0; --k) {
+        double s = (r == k) ? 1.0 : 0.0;
+#pragma unroll
+        for (int m = k + 1; m < 8; ++m) s = fma(-a[m][k], y[m], s);
+        y[k] = s * di[k];
+    }
+    double2 o;
+    o.x = (q == 0) ? y[0] : (q == 1) ? y[2] : (q == 2) ? y[4] : y[6];
+    o.y = (q == 0) ? y[1] : (q == 1) ? y[3] : (q == 2) ? y[5] : y[7];
+    return o;
+}
+
+template <int NT>
+struct WarpLayout {
+    static constexpr int DSP = 8 * NT, NL = NT * (NT + 1) / 2, NF = NT * NT, FT = NL + 2 * NF;
+    __host__ __device__ static constexpr int low(int i, int j) { return i * (i + 1) / 2 + j; }
+};
+
+template <int NT>
+__global__ void __launch_bounds__(32) traj_solve_warp(const TrajParams p) {
+    using LY = WarpLayout<NT>;
+    constexpr int DSP = LY::DSP, NL = LY::NL, NF = LY::NF, FT = LY::FT;
+    const int lane = threadIdx.x, r = lane >> 2, q = lane & 3;
+    const int Ds = p.Ds, D2 = 2 * Ds;
+    const bool even = (Ds & 1) == 0;
+    const int64_t c0 = p.chunk_off[blockIdx.x];
+    const int T = (int)(p.chunk_off[blockIdx.x + 1] - c0);
+    if (T <= 0) return;
+
+    __shared__ __align__(16) double2 sLinv[2][NL][32];   // Linv_{t-1}, Linv_{t-2} by parity of t
+    __shared__ __align__(16) double2 sLp[NF][32];        // L[t-1][t-2]
+    __shared__ __align__(16) double sdiag[64];
+    __shared__ __align__(16) double sz[3][DSP];
+    __shared__ __align__(16) double sw[DSP];
+
+    const int32_t* mh = p.mhat + c0;
+    const double* gv = p.Gv + c0 * D2;
+    double2* const Fb = reinterpret_cast<double2*>(p.Lst) + (size_t)c0 * FT * 32 + lane;
+    double* Zg = p.Z + c0 * Ds;
+
+    for (int e = lane; e < 3 * DSP; e += 32) (&sz[0][0])[e] = 0.0;
+    __syncwarp();
+    bool rok[NT], c0ok[NT], c1ok[NT];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+        rok[i] = 8 * i + r < Ds;
+        c0ok[i] = 8 * i + 2 * q < Ds;
+        c1ok[i] = 8 * i + 2 * q + 1 < Ds;
+    }
+    // elements [Aoff + 8i + r][Boff + 8j + 2q + {0,1}] of a symmetric P: adjacent in memory when
+    // read through the transposed position
+    const size_t lofs = (size_t)r * D2 + 2 * q;
+    auto ldq = [&](const double* Pm, int Aoff, int Boff, int i, int j) -> double2 {
+        double2 o = zero2();
+        const double* s = Pm + lofs + (Boff + 8 * j) + (size_t)(Aoff + 8 * i) * D2;
+        if (even) {
+            if (rok[i] && c0ok[j]) o = __ldg(reinterpret_cast<const double2*>(s));
+        } else {
+            if (rok[i] && c0ok[j]) o.x = __ldg(s);
+            if (rok[i] && c1ok[j]) o.y = __ldg(s + 1);
+        }
+        return o;
+    };
+
+    // =========================== forward: block Cholesky + L z = r ===========================
+    for (int t = 0; t < T; ++t) {
+        const double* Pt = p.P + (size_t)mh[t] * D2 * D2;
+        const double* Pm = (t >= 1) ? p.P + (size_t)mh[t - 1] * D2 * D2 : Pt;
+        const double* Pp = (t + 1 < T) ? p.P + (size_t)mh[t + 1] * D2 * D2 : Pt;
+        const double2(*const Linv1)[32] = sLinv[(t + 1) & 1];
+        const double2(*const Linv2)[32] = sLinv[t & 1];
+        double2(*const LinvT)[32] = sLinv[t & 1];          // Linv_t replaces Linv_{t-2}
+        double* const zt = sz[t % 3];
+        const double* const z1 = sz[(t + 2) % 3];
+        const double* const z2 = sz[(t + 1) % 3];
+        double2* const F = Fb + (size_t)t * FT * 32;
+
+        // ---- R[t][t-2] = -1/4 Pdd_{t-1}
+        double2 R2[NF];
+#pragma unroll
+        for (int e = 0; e < NF; ++e) R2[e] = zero2();
+        if (t >= 1) {
+#pragma unroll
+            for (int i = 0; i < NT; ++i)
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    const double2 v = ldq(Pm, Ds, Ds, i, j);
+                    R2[i * NT + j] = make_double2(-0.25 * v.x, -0.25 * v.y);
+                }
+        }
+        // ---- 1. G2 = L[t][t-2] = R2 Linv_{t-2}'
+        double2 G2[NF];
+#pragma unroll
+        for (int e = 0; e < NF; ++e) G2[e] = zero2();
+        if (t >= 2) {
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int k = 0; k <= j; ++k) {
+                    const double2 y = Linv2[LY::low(j, k)][lane];
+#pragma unroll
+                    for (int i = 0; i < NT; ++i) mma2(G2[i * NT + j], R2[i * NT + k], y);
+                }
+        }
+        // ---- 2. Tm = R[t][t-1] - G2 L[t-1][t-2]',  R[t][t-1] = 1/2 Pds_{t-1} - 1/2 Psd_t
+        double2 Tm[NF];
+#pragma unroll
+        for (int e = 0; e < NF; ++e) Tm[e] = zero2();
+        if (t >= 1) {
+#pragma unroll
+            for (int i = 0; i < NT; ++i)
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    const double2 a = ldq(Pm, Ds, 0, i, j), b = ldq(Pt, 0, Ds, i, j);
+                    Tm[i * NT + j] = make_double2(0.5 * a.x - 0.5 * b.x, 0.5 * a.y - 0.5 * b.y);
+                }
+        }
+        if (t >= 2) {
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int k = 0; k < NT; ++k) {
+                    const double2 ny = neg2(sLp[j * NT + k][lane]);
+#pragma unroll
+                    for (int i = 0; i < NT; ++i) mma2(Tm[i * NT + j], G2[i * NT + k], ny);
+                }
+        }
+        // ---- 3. G1 = L[t][t-1] = Tm Linv_{t-1}'
+        double2 G1[NF];
+#pragma unroll
+        for (int e = 0; e < NF; ++e) G1[e] = zero2();
+        if (t >= 1) {
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int k = 0; k <= j; ++k) {
+                    const double2 y = Linv1[LY::low(j, k)][lane];
+#pragma unroll
+                    for (int i = 0; i < NT; ++i) mma2(G1[i * NT + j], Tm[i * NT + k], y);
+                }
+        }
+        // ---- 4. S = R[t][t] - G2 G2' - G1 G1'   (lower tiles),
+        //         R[t][t] = Pss_t + 1/4 Pdd_{t-1} + 1/4 Pdd_{t+1};  1/4 Pdd_{t-1} = -R2
+        double2 S[NL];
+#pragma unroll
+        for (int i = 0; i < NT; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                double2 v = ldq(Pt, 0, 0, i, j);
+                v.x -= R2[i * NT + j].x;
+                v.y -= R2[i * NT + j].y;
+                if (t + 1 < T) {
+                    const double2 u = ldq(Pp, Ds, Ds, i, j);
+                    v.x = fma(0.25, u.x, v.x);
+                    v.y = fma(0.25, u.y, v.y);
+                }
+                if (i == j && !rok[i]) {      // unit diagonal in the padding
+                    if (r == 2 * q) v.x = 1.0;
+                    if (r == 2 * q + 1) v.y = 1.0;
+                }
+                S[LY::low(i, j)] = v;
+            }
+        if (t >= 1) {
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int k = 0; k < NT; ++k) {
+                    const double2 n1 = neg2(G1[j * NT + k]), n2 = neg2(G2[j * NT + k]);
+#pragma unroll
+                    for (int i = j; i < NT; ++i) {
+                        mma2(S[LY::low(i, j)], G1[i * NT + k], n1);
+                        if (t >= 2) mma2(S[LY::low(i, j)], G2[i * NT + k], n2);
+                    }
+                }
+        }
+        // ---- 4b. w = r_t - G1 z_{t-1} - G2 z_{t-2};  stream G1, G2 out; G1 becomes L[t][t-1] of
+        //          the next step
+        {
+            double acc[NT];
+#pragma unroll
+            for (int i = 0; i < NT; ++i) acc[i] = 0.0;
+            if (t >= 1) {
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    const double2 a = *reinterpret_cast<const double2*>(z1 + 8 * j + 2 * q);
+                    const double2 b = *reinterpret_cast<const double2*>(z2 + 8 * j + 2 * q);
+#pragma unroll
+                    for (int i = 0; i < NT; ++i) {
+                        acc[i] = fma(G1[i * NT + j].x, a.x, acc[i]);
+                        acc[i] = fma(G1[i * NT + j].y, a.y, acc[i]);
+                        acc[i] = fma(G2[i * NT + j].x, b.x, acc[i]);
+                        acc[i] = fma(G2[i * NT + j].y, b.y, acc[i]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NT; ++i) {
+                acc[i] += __shfl_xor_sync(kFull, acc[i], 1);
+                acc[i] += __shfl_xor_sync(kFull, acc[i], 2);
+                double rr = 0.0;
+                if (rok[i]) {
+                    const int a = 8 * i + r;
+                    rr = gv[(size_t)t * D2 + a];
+                    if (t >= 1) rr = fma(0.5, gv[(size_t)(t - 1) * D2 + Ds + a], rr);
+                    if (t + 1 < T) rr = fma(-0.5, gv[(size_t)(t + 1) * D2 + Ds + a], rr);
+                }
+                if (q == 0) sw[8 * i + r] = rr - acc[i];
+            }
+#pragma unroll
+            for (int e = 0; e < NF; ++e) {
+                F[(NL + e) * 32] = G1[e];
+                F[(NL + NF + e) * 32] = G2[e];
+                sLp[e][lane] = G1[e];       // all reads of the old L[t-1][t-2] are complete (warp-synchronous)
+            }
+        }
+        // ---- 5. blocked Cholesky of S fused with Linv_t = L^-1 (U[j][k] = Linv[k][j]')
+        double2 Li[NL], Lpan[NL], U[NL];
+#pragma unroll
+        for (int kb = 0; kb < NT; ++kb) {
+            const double2 Dinv = diag_inverse(S[LY::low(kb, kb)], sdiag, r, q, p.err);
+            Li[LY::low(kb, kb)] = Dinv;
+            if (kb + 1 < NT) U[LY::low(kb, kb)] = tile_transpose(Dinv, r, q);
+#pragma unroll
+            for (int i = kb + 1; i < NT; ++i) {        // panel L[i][kb] = S[i][kb] Dinv'
+                double2 c = zero2();
+                mma2(c, S[LY::low(i, kb)], Dinv);
+                Lpan[LY::low(i, kb)] = c;
+            }
+#pragma unroll
+            for (int j = kb + 1; j < NT; ++j) {        // trailing update
+                const double2 nj = neg2(Lpan[LY::low(j, kb)]);
+#pragma unroll
+                for (int i = j; i < NT; ++i) mma2(S[LY::low(i, j)], Lpan[LY::low(i, kb)], nj);
+            }
+#pragma unroll
+            for (int j = 0; j < kb; ++j) {             // Linv[kb][j] = -Dinv sum_k L[kb][k] Linv[k][j]
+                double2 mt = zero2();                  // M' = sum_k U[j][k] L[kb][k]'
+#pragma unroll
+                for (int k = j; k < kb; ++k) mma2(mt, U[LY::low(k, j)], Lpan[LY::low(kb, k)]);
+                const double2 nmt = neg2(mt);
+                double2 c = zero2();
+                mma2(c, Dinv, nmt);
+                Li[LY::low(kb, j)] = c;
+                if (kb + 1 < NT) {
+                    double2 u = zero2();
+                    mma2(u, nmt, Dinv);
+                    U[LY::low(kb, j)] = u;             // stored at (max, min): U[j][kb]
+                }
+            }
+        }
+        // ---- 6. z_t = Linv_t w;  publish Linv_t
+        __syncwarp();
+        {
+            double acc[NT];
+#pragma unroll
+            for (int i = 0; i < NT; ++i) acc[i] = 0.0;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const double2 w = *reinterpret_cast<const double2*>(sw + 8 * j + 2 * q);
+#pragma unroll
+                for (int i = j; i < NT; ++i) {
+                    acc[i] = fma(Li[LY::low(i, j)].x, w.x, acc[i]);
+                    acc[i] = fma(Li[LY::low(i, j)].y, w.y, acc[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NT; ++i) {
+                acc[i] += __shfl_xor_sync(kFull, acc[i], 1);
+                acc[i] += __shfl_xor_sync(kFull, acc[i], 2);
+                if (q == 0) {
+                    zt[8 * i + r] = acc[i];
+                    if (rok[i]) Zg[(size_t)t * Ds + 8 * i + r] = acc[i];
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < NL; ++e) {
+                F[e * 32] = Li[e];
+                LinvT[e][lane] = Li[e];
+            }
+        }
+        __syncwarp();
+    }
+
+    // =========================== backward: L' y = z ===========================================
+    // y_t = Linv_t' (z_t - L[t+1][t]' y_{t+1} - L[t+2][t]' y_{t+2}); the transposed products reduce
+    // over the row index r (lanes 4, 8, 16 apart) and leave their result in column layout.
+    double* const sy = &sz[0][0];   // ring of three, row-layout reads
+#pragma unroll
+    for (int e = 0; e < 3 * DSP; e += 32)
+        if (e + lane < 3 * DSP) sy[e + lane] = 0.0;
+    __syncwarp();
+    auto load_step = [&](int t, double2* L, double2* A1, double2* A2, double* zr) {
+        const double2* F = Fb + (size_t)t * FT * 32;
+#pragma unroll
+        for (int e = 0; e < NL; ++e) L[e] = F[e * 32];
+#pragma unroll
+        for (int e = 0; e < NF; ++e) {
+            A1[e] = (t + 1 < T) ? F[(FT + NL + e) * 32] : zero2();
+            A2[e] = (t + 2 < T) ? F[(2 * FT + NL + NF + e) * 32] : zero2();
+        }
+#pragma unroll
+        for (int i = 0; i < NT; ++i) zr[i] = rok[i] ? Zg[(size_t)t * Ds + 8 * i + r] : 0.0;
+    };
+    auto back_step = [&](int t, const double2* L, const double2* A1, const double2* A2, const double* zr) {
+        const double* const y1 = sy + ((t + 1) % 3) * DSP;
+        const double* const y2 = sy + ((t + 2) % 3) * DSP;
+        double* const yt = sy + (t % 3) * DSP;
+        double2 acc[NT];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[j] = zero2();
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            const double a = y1[8 * i + r], b = y2[8 * i + r];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                acc[j].x = fma(A1[i * NT + j].x, a, acc[j].x);
+                acc[j].y = fma(A1[i * NT + j].y, a, acc[j].y);
+                acc[j].x = fma(A2[i * NT + j].x, b, acc[j].x);
+                acc[j].y = fma(A2[i * NT + j].y, b, acc[j].y);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+#pragma unroll
+            for (int s = 4; s < 32; s <<= 1) {
+                acc[j].x += __shfl_xor_sync(kFull, acc[j].x, s);
+                acc[j].y += __shfl_xor_sync(kFull, acc[j].y, s);
+            }
+            if (r == 0) *reinterpret_cast<double2*>(sw + 8 * j + 2 * q) = acc[j];
+        }
+        __syncwarp();
+        double2 out[NT];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) out[j] = zero2();
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            const double w = zr[i] - sw[8 * i + r];
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                out[j].x = fma(L[LY::low(i, j)].x, w, out[j].x);
+                out[j].y = fma(L[LY::low(i, j)].y, w, out[j].y);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+#pragma unroll
+            for (int s = 4; s < 32; s <<= 1) {
+                out[j].x += __shfl_xor_sync(kFull, out[j].x, s);
+                out[j].y += __shfl_xor_sync(kFull, out[j].y, s);
+            }
+            if (r == 0) {
+                *reinterpret_cast<double2*>(yt + 8 * j + 2 * q) = out[j];
+                double* yg = p.Y + (c0 + t) * p.ldy + 8 * j + 2 * q;   // reshape(y, D, T)  src/trajectory_gmmmap.jl:109
+                if (c0ok[j]) yg[0] = out[j].x;
+                if (c1ok[j]) yg[1] = out[j].y;
+            }
+        }
+        if (p.copy_power && lane == 31) p.Y[(c0 + t) * p.ldy - 1] = p.Xpow[(c0 + t) * p.ldx - 1];  // src/common.jl:60
+        __syncwarp();
+    };
+    {
+        double2 La[NL], A1a[NF], A2a[NF], Lb[NL], A1b[NF], A2b[NF];
+        double za[NT], zb[NT];
+        int t = T - 1;
+        load_step(t, La, A1a, A2a, za);
+        for (; t >= 1; t -= 2) {
+            load_step(t - 1, Lb, A1b, A2b, zb);
+            back_step(t, La, A1a, A2a, za);
+            if (t >= 2) load_step(t - 2, La, A1a, A2a, za);
+            back_step(t - 1, Lb, A1b, A2b, zb);
+        }
+        if (t == 0) back_step(0, La, A1a, A2a, za);
+    }
+}
+
+template <int NT>
+int32_t launch_warp(const TrajParams& p, int64_t nchunks, cudaStream_t st) {
+    traj_solve_warp<NT><<<(unsigned)nchunks, 32, 0, st>>>(p);
+    count_launch();
+    VCB_CUDA(cudaGetLastError());
+    return VCB_OK;
+}
+
+}  // namespace
+
+size_t traj_warp_factor_bytes(int Ds) {
+    const int nt = (Ds + 7) / 8;
+    if (nt < 1 || nt > 3) return 0;
+    return (size_t)(nt * (nt + 1) / 2 + 2 * nt * nt) * 32 * sizeof(double2);
+}
+
+int32_t traj_warp_launch(const TrajParams& p, int64_t nchunks, cudaStream_t st) {
+    switch ((p.Ds + 7) / 8) {
+        case 1: return launch_warp<1>(p, nchunks, st);
+        case 2: return launch_warp<2>(p, nchunks, st);
+        case 3: return launch_warp<3>(p, nchunks, st);
+        default: return fail(VCB_EUNSUPPORTED, "warp trajectory solver covers static dimension <= 24 (got %d)", p.Ds);
+    }
+}
+
+}  // namespace vcb
