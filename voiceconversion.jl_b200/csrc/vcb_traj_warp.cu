@@ -75,13 +75,14 @@ __device__ __forceinline__ double2 diag_inverse(const double2 d, double* sd, int
             for (int c2 = c + 1; c2 <= i; ++c2) a[i][c2] = fma(-a[i][c], a[c2][c], a[i][c2]);
     }
     if (bad) atomicExch(err, 1);
-    double y[8];
+    double y[8], s[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] = (r == k) ? 1.0 : 0.0;
 #pragma unroll
     for (int k = 7; k >= 0; --k) {
-        double s = (r == k) ? 1.0 : 0.0;
+        y[k] = s[k] * di[k];
 #pragma unroll
-        for (int m = k + 1; m < 8; ++m) s = fma(-a[m][k], y[m], s);
-        y[k] = s * di[k];
+        for (int m = 0; m < k; ++m) s[m] = fma(-a[k][m], y[k], s[m]);
     }
     double2 o;
     o.x = (q == 0) ? y[0] : (q == 1) ? y[2] : (q == 2) ? y[4] : y[6];
@@ -95,13 +96,23 @@ struct WarpLayout {
     __host__ __device__ static constexpr int low(int i, int j) { return i * (i + 1) / 2 + j; }
 };
 
-template <int NT>
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(a), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// FULL: Ds == 8 NT (no padding, every 16-byte piece aligned): the 39 P tiles a step assembles its
+// R blocks from are prefetched into shared memory with cp.async during the previous step -- one
+// piece per lane and tile, read back only by the lane that requested it.
+template <int NT, bool FULL>
 __global__ void __launch_bounds__(32) traj_solve_warp(const TrajParams p) {
     using LY = WarpLayout<NT>;
     constexpr int DSP = LY::DSP, NL = LY::NL, NF = LY::NF, FT = LY::FT;
     const int lane = threadIdx.x, r = lane >> 2, q = lane & 3;
     const int Ds = p.Ds, D2 = 2 * Ds;
-    const bool even = (Ds & 1) == 0;
+    const bool even = FULL || (Ds & 1) == 0;
     const int64_t c0 = p.chunk_off[blockIdx.x];
     const int T = (int)(p.chunk_off[blockIdx.x + 1] - c0);
     if (T <= 0) return;
@@ -111,6 +122,8 @@ __global__ void __launch_bounds__(32) traj_solve_warp(const TrajParams p) {
     __shared__ __align__(16) double sdiag[64];
     __shared__ __align__(16) double sz[3][DSP];
     __shared__ __align__(16) double sw[DSP];
+    constexpr int NPT = 3 * NF + 2 * NL;                 // Pdd_{t-1}, Pds_{t-1}, Psd_t | Pss_t, Pdd_{t+1} (lower)
+    __shared__ __align__(16) double2 sP[FULL ? NPT : 1][32];
 
     const int32_t* mh = p.mhat + c0;
     const double* gv = p.Gv + c0 * D2;
@@ -122,9 +135,9 @@ __global__ void __launch_bounds__(32) traj_solve_warp(const TrajParams p) {
     bool rok[NT], c0ok[NT], c1ok[NT];
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
-        rok[i] = 8 * i + r < Ds;
-        c0ok[i] = 8 * i + 2 * q < Ds;
-        c1ok[i] = 8 * i + 2 * q + 1 < Ds;
+        rok[i] = FULL || 8 * i + r < Ds;
+        c0ok[i] = FULL || 8 * i + 2 * q < Ds;
+        c1ok[i] = FULL || 8 * i + 2 * q + 1 < Ds;
     }
     // elements [Aoff + 8i + r][Boff + 8j + 2q + {0,1}] of a symmetric P: adjacent in memory when
     // read through the transposed position
@@ -141,6 +154,28 @@ __global__ void __launch_bounds__(32) traj_solve_warp(const TrajParams p) {
         return o;
     };
 
+    auto prefetch = [&](int tn) {
+        const double* Pa = p.P + (size_t)mh[tn >= 1 ? tn - 1 : 0] * D2 * D2 + lofs;
+        const double* Pb = p.P + (size_t)mh[tn] * D2 * D2 + lofs;
+        const double* Pc = p.P + (size_t)mh[tn + 1 < T ? tn + 1 : tn] * D2 * D2 + lofs;
+        const size_t dd = (size_t)Ds * D2 + Ds, ds = (size_t)Ds * D2, sd = Ds;
+#pragma unroll
+        for (int i = 0; i < NT; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const size_t o = 8 * j + (size_t)(8 * i) * D2;
+                cp_async16(&sP[i * NT + j][lane], Pa + dd + o);
+                cp_async16(&sP[NF + i * NT + j][lane], Pa + ds + o);
+                cp_async16(&sP[2 * NF + i * NT + j][lane], Pb + sd + o);
+                if (j <= i) {
+                    cp_async16(&sP[3 * NF + LY::low(i, j)][lane], Pb + o);
+                    cp_async16(&sP[3 * NF + NL + LY::low(i, j)][lane], Pc + dd + o);
+                }
+            }
+        cp_async_commit();
+    };
+    if (FULL) prefetch(0);
+
     // =========================== forward: block Cholesky + L z = r ===========================
     for (int t = 0; t < T; ++t) {
         const double* Pt = p.P + (size_t)mh[t] * D2 * D2;
@@ -153,6 +188,23 @@ __global__ void __launch_bounds__(32) traj_solve_warp(const TrajParams p) {
         const double* const z1 = sz[(t + 2) % 3];
         const double* const z2 = sz[(t + 1) % 3];
         double2* const F = Fb + (size_t)t * FT * 32;
+        double rr[NT];          // r_t = u_t + 1/2 v_{t-1} - 1/2 v_{t+1}, rows 8i + r (issued early, used in 4b)
+        {
+            const double wm = (t >= 1) ? 0.5 : 0.0, wp = (t + 1 < T) ? -0.5 : 0.0;
+            const double* g0 = gv + (size_t)t * D2, *gm = gv + (size_t)(t >= 1 ? t - 1 : t) * D2 + Ds;
+            const double* gp = gv + (size_t)(t + 1 < T ? t + 1 : t) * D2 + Ds;
+#pragma unroll
+            for (int i = 0; i < NT; ++i) {
+                rr[i] = 0.0;
+                if (rok[i]) rr[i] = fma(wp, gp[8 * i + r], fma(wm, gm[8 * i + r], g0[8 * i + r]));
+            }
+        }
+        if (FULL) cp_async_wait_all();
+        auto Pddm = [&](int i, int j) { return FULL ? sP[i * NT + j][lane] : ldq(Pm, Ds, Ds, i, j); };
+        auto Pdsm = [&](int i, int j) { return FULL ? sP[NF + i * NT + j][lane] : ldq(Pm, Ds, 0, i, j); };
+        auto Psdt = [&](int i, int j) { return FULL ? sP[2 * NF + i * NT + j][lane] : ldq(Pt, 0, Ds, i, j); };
+        auto Psst = [&](int i, int j) { return FULL ? sP[3 * NF + LY::low(i, j)][lane] : ldq(Pt, 0, 0, i, j); };
+        auto Pddp = [&](int i, int j) { return FULL ? sP[3 * NF + NL + LY::low(i, j)][lane] : ldq(Pp, Ds, Ds, i, j); };
 
         // ---- R[t][t-2] = -1/4 Pdd_{t-1}
         double2 R2[NF];
@@ -163,7 +215,7 @@ __global__ void __launch_bounds__(32) traj_solve_warp(const TrajParams p) {
             for (int i = 0; i < NT; ++i)
 #pragma unroll
                 for (int j = 0; j < NT; ++j) {
-                    const double2 v = ldq(Pm, Ds, Ds, i, j);
+                    const double2 v = Pddm(i, j);
                     R2[i * NT + j] = make_double2(-0.25 * v.x, -0.25 * v.y);
                 }
         }
@@ -190,7 +242,7 @@ __global__ void __launch_bounds__(32) traj_solve_warp(const TrajParams p) {
             for (int i = 0; i < NT; ++i)
 #pragma unroll
                 for (int j = 0; j < NT; ++j) {
-                    const double2 a = ldq(Pm, Ds, 0, i, j), b = ldq(Pt, 0, Ds, i, j);
+                    const double2 a = Pdsm(i, j), b = Psdt(i, j);
                     Tm[i * NT + j] = make_double2(0.5 * a.x - 0.5 * b.x, 0.5 * a.y - 0.5 * b.y);
                 }
         }
@@ -225,11 +277,19 @@ __global__ void __launch_bounds__(32) traj_solve_warp(const TrajParams p) {
         for (int i = 0; i < NT; ++i)
 #pragma unroll
             for (int j = 0; j <= i; ++j) {
-                double2 v = ldq(Pt, 0, 0, i, j);
-                v.x -= R2[i * NT + j].x;
-                v.y -= R2[i * NT + j].y;
+                double2 v = Psst(i, j);
+                if (FULL) {       // R2 is dead by now: re-read the tile rather than keep it in registers
+                    if (t >= 1) {
+                        const double2 u = Pddm(i, j);
+                        v.x = fma(0.25, u.x, v.x);
+                        v.y = fma(0.25, u.y, v.y);
+                    }
+                } else {
+                    v.x -= R2[i * NT + j].x;
+                    v.y -= R2[i * NT + j].y;
+                }
                 if (t + 1 < T) {
-                    const double2 u = ldq(Pp, Ds, Ds, i, j);
+                    const double2 u = Pddp(i, j);
                     v.x = fma(0.25, u.x, v.x);
                     v.y = fma(0.25, u.y, v.y);
                 }
@@ -239,6 +299,7 @@ __global__ void __launch_bounds__(32) traj_solve_warp(const TrajParams p) {
                 }
                 S[LY::low(i, j)] = v;
             }
+        if (FULL && t + 1 < T) prefetch(t + 1);     // every tile of this step has been consumed
         if (t >= 1) {
 #pragma unroll
             for (int j = 0; j < NT; ++j)
@@ -276,14 +337,7 @@ __global__ void __launch_bounds__(32) traj_solve_warp(const TrajParams p) {
             for (int i = 0; i < NT; ++i) {
                 acc[i] += __shfl_xor_sync(kFull, acc[i], 1);
                 acc[i] += __shfl_xor_sync(kFull, acc[i], 2);
-                double rr = 0.0;
-                if (rok[i]) {
-                    const int a = 8 * i + r;
-                    rr = gv[(size_t)t * D2 + a];
-                    if (t >= 1) rr = fma(0.5, gv[(size_t)(t - 1) * D2 + Ds + a], rr);
-                    if (t + 1 < T) rr = fma(-0.5, gv[(size_t)(t + 1) * D2 + Ds + a], rr);
-                }
-                if (q == 0) sw[8 * i + r] = rr - acc[i];
+                if (q == 0) sw[8 * i + r] = rr[i] - acc[i];
             }
 #pragma unroll
             for (int e = 0; e < NF; ++e) {
@@ -454,7 +508,13 @@ __global__ void __launch_bounds__(32) traj_solve_warp(const TrajParams p) {
 
 template <int NT>
 int32_t launch_warp(const TrajParams& p, int64_t nchunks, cudaStream_t st) {
-    traj_solve_warp<NT><<<(unsigned)nchunks, 32, 0, st>>>(p);
+    if (p.Ds == 8 * NT) {
+        auto k = traj_solve_warp<NT, true>;
+        VCB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        k<<<(unsigned)nchunks, 32, 0, st>>>(p);
+    } else {
+        traj_solve_warp<NT, false><<<(unsigned)nchunks, 32, 0, st>>>(p);
+    }
     count_launch();
     VCB_CUDA(cudaGetLastError());
     return VCB_OK;
