@@ -459,7 +459,7 @@ gmm_tc_kernel(const TcParams p) {
         const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
         constexpr int LOADW = (ROWS <= 64) ? ROWS : 32;   // TMEM columns fetched per wait
         int64_t it = 0;
-        long long w_full = 0, w_part = 0;
+        long long w_full = 0, w_part = 0, w_ld = 0;
         const long long t_begin = clock64();
         for (int64_t tl = 0; tl < my_tiles; ++tl) {
             const int64_t tile = blockIdx.x + tl * gridDim.x;
@@ -474,6 +474,7 @@ gmm_tc_kernel(const TcParams p) {
             for (int c = 0; c < NCH; ++c, ++it) {
                 const int acc = (int)(it & 1);
                 const uint32_t accph = (uint32_t)((it >> 1) & 1);
+                const float* const cst_c = p.cst + c * p.G;
                 TIMED_WAIT(acc_full(acc), accph, w_full);
                 tc_fence_after();
                 const uint32_t tcol = tmem_base + lane_base + (uint32_t)(acc * N);
@@ -487,49 +488,72 @@ gmm_tc_kernel(const TcParams p) {
                         const uint32_t mcol = tcol + (uint32_t)(g * ROWS);
                         tmem_ld_cols<LOADW>(mcol, v);
                     };
-                    auto reduce = [&](const float (&v)[LOADW], int g) {
-                        const int m = c * p.G + g;
-                        const float cm = p.cst[m];  // -inf for padding mixtures
-                        float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+                    // Two mixtures are reduced together so their dependent chains (|z|^2, the
+                    // exponentials) overlap.  The running maximum is lazy: it moves only when a
+                    // log-likelihood exceeds it by more than kLazy, so the 24-wide rescale of the
+                    // partial sums is rare instead of once per mixture (weights up to e^kLazy are
+                    // far inside fp32 range, and the relative accuracy of a weight does not depend
+                    // on the reference point).
+                    constexpr float kLazy = 40.0f;
+                    auto reduce2 = [&](const float (&va)[LOADW], const float (&vb)[LOADW], int g, bool two, float cma, float cmb) {
+                        float qa0 = 0.f, qa1 = 0.f, qb0 = 0.f, qb1 = 0.f;
 #pragma unroll
-                        for (int r = 0; r < DP; r += 4) {
-                            q0 = fmaf(v[r], v[r], q0);
-                            q1 = fmaf(v[r + 1], v[r + 1], q1);
-                            q2 = fmaf(v[r + 2], v[r + 2], q2);
-                            q3 = fmaf(v[r + 3], v[r + 3], q3);
+                        for (int r = 0; r < DP; r += 2) {
+                            qa0 = fmaf(va[r], va[r], qa0);
+                            qa1 = fmaf(va[r + 1], va[r + 1], qa1);
+                            qb0 = fmaf(vb[r], vb[r], qb0);
+                            qb1 = fmaf(vb[r + 1], vb[r + 1], qb1);
                         }
-                        const float q = (q0 + q1) + (q2 + q3);
-                        const float l = fmaf(-0.5f, q, cm);
+                        const float qa = qa0 + qa1, qb = qb0 + qb1;
+                        const float la = fmaf(-0.5f, qa, cma);
+                        const float lb = two ? fmaf(-0.5f, qb, cmb) : -INFINITY;
                         if (CONVERT) {
-                            if (l > mx) {
-                                const float a = __expf(mx - l);
+                            const float lm = fmaxf(la, lb);
+                            if (lm > mx + kLazy) {
+                                const float a = __expf(mx - lm);   // 0 on the first visit (mx = -inf)
                                 sum *= a;
 #pragma unroll
                                 for (int r = 0; r < DP; ++r) y[r] *= a;
-                                mx = l;
+                                mx = lm;
                             }
-                            const float w = (l == -INFINITY) ? 0.f : __expf(l - mx);
-                            sum += w;
+                            const float wa = (la == -INFINITY) ? 0.f : __expf(la - mx);
+                            const float wb = (lb == -INFINITY) ? 0.f : __expf(lb - mx);
+                            sum += wa + wb;
 #pragma unroll
-                            for (int r = 0; r < DP; ++r) y[r] = fmaf(w, v[(CONVERT ? DP : 0) + r], y[r]);
+                            for (int r = 0; r < DP; ++r)
+                                y[r] = fmaf(wa, va[(CONVERT ? DP : 0) + r], fmaf(wb, vb[(CONVERT ? DP : 0) + r], y[r]));
                         } else {
-                            if (l > mx) { second = mx; mx = l; best = m; qbest = q; }
-                            else if (l > second) second = l;
+                            const int m = c * p.G + g;
+                            if (la > mx) { second = mx; mx = la; best = m; qbest = qa; }
+                            else if (la > second) second = la;
+                            if (lb > mx) { second = mx; mx = lb; best = m + kEpiGroups; qbest = qb; }
+                            else if (lb > second) second = lb;
                         }
                     };
                     // both groups drain the same chunk: group e takes mixtures e, e + kEpiGroups, ...
-                    // Two mixtures' columns are requested before either is reduced: with the MMA
-                    // of the other stage running, a TMEM load takes several hundred cycles, far
-                    // longer than reducing one mixture, so the loads must overlap each other.
                     constexpr int GS = kEpiGroups;
                     float v0[LOADW], v1[LOADW];
+                    bool released = false;
                     for (int g = group; g < p.G; g += 2 * GS) {
+                        const bool two = g + GS < p.G;
+                        const float cma = cst_c[g], cmb = two ? cst_c[g + GS] : -INFINITY;   // in flight under the TMEM loads
+                        const long long tl0 = p.prof ? clock64() : 0;
                         fetch(v0, g);
-                        if (g + GS < p.G) fetch(v1, g + GS);
+                        if (two) fetch(v1, g + GS);
                         tmem_ld_wait();
-                        reduce(v0, g);
-                        if (g + GS < p.G) reduce(v1, g + GS);
+                        if (p.prof) w_ld += clock64() - tl0;
+                        if (g + 2 * GS >= p.G) {
+                            // this group's last columns of the stage are in registers: hand the
+                            // accumulator back before reducing them, so the stage is held for the
+                            // TMEM read only and the MMA of chunk c+2 overlaps this arithmetic
+                            tc_fence_before();
+                            mbar_arrive(acc_empty(acc));
+                            released = true;
+                        }
+                        reduce2(v0, v1, g, two, cma, cmb);
                     }
+                    if (!released) { tc_fence_before(); mbar_arrive(acc_empty(acc)); }
+                    continue;
                 } else {
                 for (int g = group; g < p.G; g += kEpiGroups) {
                     const int m = c * p.G + g;
@@ -636,6 +660,7 @@ gmm_tc_kernel(const TcParams p) {
         if (p.prof && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 128)) {
             const int o = threadIdx.x == 0 ? 6 : 9;
             p.prof[o] = w_full; p.prof[o + 1] = w_part; p.prof[o + 2] = clock64() - t_begin;
+            p.prof[threadIdx.x == 0 ? 14 : 15] = w_ld;
         }
     }
 
@@ -680,8 +705,8 @@ int32_t launch_tc(const TcParams& p_in, size_t smem, cudaStream_t st) {
         long long h[16];
         cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
         cudaFree(d_prof);
-        fprintf(stderr, "[tc prof CTA0] producer: wait b_empty %lld of %lld | mma: wait a_full %lld b_full %lld acc_empty %lld of %lld | epi0: wait acc_full %lld part %lld of %lld | epi1: wait acc_full %lld part %lld of %lld | loader: wait a_empty %lld of %lld\n",
-                h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11], h[12], h[13]);
+        fprintf(stderr, "[tc prof CTA0] producer: wait b_empty %lld of %lld | mma: wait a_full %lld b_full %lld acc_empty %lld of %lld | epi0: wait acc_full %lld part %lld of %lld | epi1: wait acc_full %lld part %lld of %lld | loader: wait a_empty %lld of %lld | tmem ld epi0 %lld epi1 %lld\n",
+                h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11], h[12], h[13], h[14], h[15]);
     }
     count_launch();
     VCB_CUDA(cudaGetLastError());
