@@ -172,6 +172,43 @@ int32_t vcb_align_batch(const double* src, const int64_t* src_off, const double*
                         const int64_t* tgt_off, int64_t npairs, int32_t D, double* newtgt,
                         int64_t* paths);
 
+
+/* ---------------------------------------------------------------------------------------------
+ * Global variance and differential models
+ * ------------------------------------------------------------------------------------------- */
+typedef struct vcb_trajgv vcb_trajgv; /* TrajectoryGVGMMMap  src/trajectory_gmmmap.jl:114-127 */
+/* TrajectoryGVGMMMap(tgmm, mu_v (Ds), S_vv (Ds,Ds)): asserts mu_v >= 0 (:124, VCB_EARG), stores
+ * inv(S_vv) (:125, VCB_ESINGULAR).  The trajectory handle is borrowed and must outlive this one. */
+int32_t vcb_trajgv_create(const vcb_traj* t, const double* mu_v, const double* sigma_vv, vcb_trajgv** out);
+int32_t vcb_trajgv_destroy(vcb_trajgv* v);
+/* fvconvert(tgv, X; epochs, alpha) (src/trajectory_gmmmap.jl:140-172) for a ragged batch, chunked
+ * like vcb_traj_convert_batch.  The reference's defaults are epochs = 100, alpha = 1.0e-5.  Chunks
+ * shorter than 2 frames are rejected (their global variance is NaN and the reference asserts). */
+int32_t vcb_trajgv_convert_batch(const vcb_trajgv* v, const double* X, int32_t xrows, int64_t ldx,
+                                 const int64_t* offsets, int64_t nseq, int32_t chunk_limit, int32_t epochs,
+                                 double alpha, double* Y, int64_t ldy);
+int32_t vcb_trajgv_convert_batch_dev(const vcb_trajgv* v, const double* dX, int32_t xrows, int64_t ldx,
+                                     const int64_t* offsets, int64_t nseq, int32_t chunk_limit, int32_t epochs,
+                                     double alpha, double* dY, int64_t ldy, void* stream);
+/* vc(c::TrajectoryConverter, fm) with the GV converter (src/common.jl:31-63): fm (1+2Ds, total) ->
+ * out (1+Ds, total), power row copied. */
+int32_t vcb_trajgv_vc_batch(const vcb_trajgv* v, const double* fm, int32_t rows, const int64_t* offsets,
+                            int64_t nseq, int32_t chunk_limit, int32_t epochs, double alpha, double* out);
+int32_t vcb_trajgv_vc_batch_dev(const vcb_trajgv* v, const double* dfm, int32_t rows, const int64_t* offsets,
+                                int64_t nseq, int32_t chunk_limit, int32_t epochs, double alpha, double* dout,
+                                void* stream);
+/* fvpostf(VarianceScaling(sigma2), src) (src/gv.jl:10-21) per utterance of a ragged batch:
+ * Y = sqrt(sigma2 ./ var(X, 2)) .* (X .- mean(X, 2)) .+ mean(X, 2); X, Y (D, total) with leading
+ * dimensions ldx, ldy; Y may alias X (fvpostf!). */
+int32_t vcb_variance_scaling_batch(const double* sigma2, int32_t D, const double* X, int64_t ldx,
+                                   const int64_t* offsets, int64_t nseq, double* Y, int64_t ldy);
+int32_t vcb_variance_scaling_batch_dev(const double* d_sigma2, int32_t D, const double* dX, int64_t ldx,
+                                       const int64_t* offsets, int64_t nseq, double* dY, int64_t ldy, void* stream);
+/* diffgmm (src/diffgmm.jl:9-25) on the joint parameters: mu (2D,M), sigma (2D,2D,M) -> the joint
+ * parameters of the differential model; feed them to vcb_gmmmap_create. Host-side, no GPU work. */
+int32_t vcb_diffgmm(const double* mu, const double* sigma, int32_t twoD, int32_t M, double* mu_out,
+                    double* sigma_out);
+
 #ifdef __cplusplus
 }
 #endif

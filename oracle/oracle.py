@@ -70,6 +70,15 @@ def lib():
         L.vco_traj_fvconvert.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int, _dp, _ip, _dp]
         L.vco_vc_traj.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int64, _dp]
         L.vco_vc_traj_batch_mt.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, _lp, C.c_int64, _dp, C.c_int]
+        L.vco_variance_scaling.argtypes = [_dp, _dp, C.c_int, C.c_int64]
+        L.vco_variance_scaling.restype = None
+        L.vco_trajgv_create.argtypes = [C.c_void_p, _dp, _dp, C.POINTER(C.c_void_p)]
+        L.vco_trajgv_destroy.argtypes = [C.c_void_p]
+        L.vco_trajgv_destroy.restype = None
+        L.vco_trajgv_fvconvert.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int, C.c_int, C.c_double, _dp]
+        L.vco_vc_trajgv.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int64, C.c_int, C.c_double, _dp]
+        L.vco_diffgmm.argtypes = [_dp, _dp, C.c_int, C.c_int, _dp, _dp]
+        L.vco_diffgmm.restype = None
         L.vco_dtw_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.vco_dtw_destroy.argtypes = [C.c_void_p]
         L.vco_dtw_destroy.restype = None
@@ -222,6 +231,54 @@ class TrajectoryGMMMap:
         out = np.empty((((rows - 1) >> 1) + 1, T), order="F")
         _check(lib().vco_vc_traj(self._h, _p(fm), rows, T, _p(out)), "vc(traj)")
         return out
+
+
+class TrajectoryGVGMMMap:
+    """src/trajectory_gmmmap.jl:112-189"""
+
+    def __init__(self, tgmm: TrajectoryGMMMap, mu_v, sigma_vv):
+        self.tgmm = tgmm
+        mu_v, sigma_vv = _f64(mu_v), _f64(sigma_vv)
+        self._h = C.c_void_p()
+        _check(lib().vco_trajgv_create(tgmm._h, _p(mu_v), _p(sigma_vv), C.byref(self._h)), "TrajectoryGVGMMMap")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().vco_trajgv_destroy(self._h)
+            self._h = None
+
+    def __len__(self):
+        return len(self.tgmm)
+
+    def fvconvert(self, X, epochs: int = 100, alpha: float = 1.0e-5):
+        X = _f64(X)
+        rows, T = X.shape
+        Y = np.empty((rows // 2, T), order="F")
+        _check(lib().vco_trajgv_fvconvert(self._h, _p(X), rows, T, epochs, alpha, _p(Y)), "fvconvert(trajgv)")
+        return Y
+
+    def vc(self, fm, epochs: int = 100, alpha: float = 1.0e-5):
+        fm = _f64(fm)
+        rows, T = fm.shape
+        out = np.empty((((rows - 1) >> 1) + 1, T), order="F")
+        _check(lib().vco_vc_trajgv(self._h, _p(fm), rows, T, epochs, alpha, _p(out)), "vc(trajgv)")
+        return out
+
+
+def fvpostf(sigma2, src):
+    """fvpostf(VarianceScaling(sigma2), src)  src/gv.jl:10-21 (returns a filtered copy)."""
+    out = _f64(src).copy(order="F")
+    s2 = _f64(sigma2)
+    lib().vco_variance_scaling(_p(s2), _p(out), out.shape[0], out.shape[1])
+    return out
+
+
+def diffgmm(means, covars):
+    """src/diffgmm.jl:9-25 applied to the joint parameters; returns (means', covars')."""
+    mu, sg = _f64(means), _f64(covars)
+    mo, so = np.empty_like(mu, order="F"), np.empty_like(sg, order="F")
+    lib().vco_diffgmm(_p(mu), _p(sg), mu.shape[0], mu.shape[1], _p(mo), _p(so))
+    return mo, so
 
 
 def vc_traj_batch(g: GMMMap, limit: int, fm, offsets, nthreads: int = 1):

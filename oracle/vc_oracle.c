@@ -480,8 +480,10 @@ static int band_lu_solve(int n, int kl, int ku, double* ab, double* b) {
 }
 
 /* src/trajectory_gmmmap.jl:65-110 */
-int vco_traj_fvconvert(vco_traj* tg, const double* X, int xrows, int T, double* Y, int* mhat_out,
-                       double* Ey_out) {
+/* keep_ab / keep_rhs (optional): malloc'ed copies of the band matrix R = W'Dy^-1 W (LAPACK band
+ * storage, before factorisation) and of r = W'Dy^-1 Ey, for the GV gradient (:150-156). */
+static int traj_core(vco_traj* tg, const double* X, int xrows, int T, double* Y, int* mhat_out,
+                     double* Ey_out, double** keep_ab, double** keep_rhs, int* kl_out, int* ldab_out) {
     vco_gmmmap* g = tg->g;
     int D2 = g->D;
     if (xrows & 1) return VCO_EDIM;
@@ -535,12 +537,179 @@ int vco_traj_fvconvert(vco_traj* tg, const double* X, int xrows, int T, double* 
         }
     }
 #undef AB
+    if (keep_ab) {
+        *keep_ab = (double*)malloc(sizeof(double) * (size_t)ldab * n);
+        *keep_rhs = (double*)malloc(sizeof(double) * (size_t)n);
+        if (!*keep_ab || !*keep_rhs) { free(mhat); free(Ey); free(ab); free(rhs); free(scratch); return VCO_ENOMEM; }
+        memcpy(*keep_ab, ab, sizeof(double) * (size_t)ldab * n);
+        memcpy(*keep_rhs, rhs, sizeof(double) * (size_t)n);
+        *kl_out = kl; *ldab_out = ldab;
+    }
     int rc = band_lu_solve(n, kl, ku, ab, rhs); /* :105  y = R \ r */
     if (rc == VCO_OK) memcpy(Y, rhs, sizeof(double) * (size_t)n); /* :109 reshape(y, D, T) */
     if (mhat_out) memcpy(mhat_out, mhat, sizeof(int) * (size_t)T);
     if (Ey_out) memcpy(Ey_out, Ey, sizeof(double) * (size_t)D2 * T);
     free(mhat); free(Ey); free(ab); free(rhs); free(scratch);
     return rc;
+}
+
+int vco_traj_fvconvert(vco_traj* tg, const double* X, int xrows, int T, double* Y, int* mhat_out,
+                       double* Ey_out) {
+    return traj_core(tg, X, xrows, T, Y, mhat_out, Ey_out, 0, 0, 0, 0);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* GV post-filter -- src/gv.jl:6-21                                                            */
+/* ------------------------------------------------------------------------------------------ */
+
+/* src[:,:] = sqrt(s2 ./ var(src, 2)) .* (src .- mean(src, 2)) .+ mean(src, 2)   (src/gv.jl:10-15)
+ * mean = sum/T, var = sum((x - mean)^2)/(T - 1) (Julia's corrected two-pass varm), both summed in
+ * frame order.  T == 1 gives NaN exactly as in Julia (0/0). */
+void vco_variance_scaling(const double* s2, double* src, int D, int64_t T) {
+    for (int i = 0; i < D; ++i) {
+        double sum = 0.0;
+        for (int64_t t = 0; t < T; ++t) sum += src[t * D + i];
+        const double mu = sum / (double)T;
+        double ss = 0.0;
+        for (int64_t t = 0; t < T; ++t) { const double d = src[t * D + i] - mu; ss += d * d; }
+        const double var = ss / (double)(T - 1);
+        const double sc = sqrt(s2[i] / var);
+        for (int64_t t = 0; t < T; ++t) src[t * D + i] = sc * (src[t * D + i] - mu) + mu;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* TrajectoryGVGMMMap -- src/trajectory_gmmmap.jl:112-189                                      */
+/* ------------------------------------------------------------------------------------------ */
+
+struct vco_trajgv {
+    vco_traj* t;   /* borrowed */
+    int Ds;
+    double* muv;   /* (Ds)      :116 */
+    double* pv;    /* (Ds,Ds)   :118  inv(Svv) */
+};
+
+void vco_trajgv_destroy(vco_trajgv* v) { if (v) { free(v->muv); free(v->pv); free(v); } }
+
+int vco_trajgv_create(vco_traj* t, const double* muv, const double* svv, vco_trajgv** out) {
+    if (!t || !muv || !svv || !out) return VCO_EARG;
+    const int Ds = t->g->D / 2;
+    for (int i = 0; i < Ds; ++i)
+        if (muv[i] < 0.0) return VCO_EARG;          /* :124  @assert sum(muv .< 0) == 0 */
+    vco_trajgv* v = (vco_trajgv*)calloc(1, sizeof(*v));
+    if (!v) return VCO_ENOMEM;
+    v->t = t; v->Ds = Ds;
+    v->muv = (double*)malloc(sizeof(double) * Ds);
+    v->pv = (double*)malloc(sizeof(double) * (size_t)Ds * Ds);
+    if (!v->muv || !v->pv) { vco_trajgv_destroy(v); return VCO_ENOMEM; }
+    memcpy(v->muv, muv, sizeof(double) * Ds);
+    memcpy(v->pv, svv, sizeof(double) * (size_t)Ds * Ds);
+    int rc = lu_inverse(v->pv, Ds);                  /* :125  inv(Svv) */
+    if (rc != VCO_OK) { vco_trajgv_destroy(v); return rc; }
+    *out = v;
+    return VCO_OK;
+}
+
+/* fvconvert(tgv, X; epochs, alpha)  :140-172, gvgrad :175-189 */
+int vco_trajgv_fvconvert(vco_trajgv* v, const double* X, int xrows, int T, int epochs, double alpha,
+                         double* Y) {
+    const int D = v->Ds;
+    double *ab = 0, *r = 0;
+    int kl = 0, ldab = 0;
+    int rc = traj_core(v->t, X, xrows, T, Y, 0, 0, &ab, &r, &kl, &ldab);   /* :146 y0 */
+    if (rc != VCO_OK) { free(ab); free(r); return rc; }
+    const int n = D * T, ku = kl;
+    vco_variance_scaling(v->muv, Y, D, T);                                   /* :150 eq. (58) */
+    const double omega = 1.0 / (2.0 * (double)T);                            /* :152 */
+    double* dy = (double*)malloc(sizeof(double) * (size_t)n);
+    double* gv = (double*)malloc(sizeof(double) * 3 * (size_t)D);
+    if (!dy || !gv) { free(ab); free(r); free(dy); free(gv); return VCO_ENOMEM; }
+    double *muy = gv + D, *coef = gv + 2 * D;
+    for (int epoch = 0; epoch < epochs; ++epoch) {
+        /* gvgrad: gv = var(y, 2), muy = mean(y, 2); v[:,t] = -2/T * (pv' (gv - muv)) .* (y[:,t] - muy) */
+        for (int i = 0; i < D; ++i) {
+            double sum = 0.0;
+            for (int t = 0; t < T; ++t) sum += Y[(size_t)t * D + i];
+            muy[i] = sum / (double)T;
+            double ss = 0.0;
+            for (int t = 0; t < T; ++t) { const double d = Y[(size_t)t * D + i] - muy[i]; ss += d * d; }
+            gv[i] = ss / (double)(T - 1);
+        }
+        for (int i = 0; i < D; ++i) {
+            double s = 0.0;
+            for (int k = 0; k < D; ++k) s += v->pv[k + (size_t)i * D] * (gv[k] - v->muv[k]);  /* pv' */
+            coef[i] = -2.0 / (double)T * s;
+        }
+        /* :161  dy = omega * (-(W'Dy^-1 W) y + W'Dy^-1 Ey) + vec(gvgrad) */
+        for (int i = 0; i < n; ++i) {
+            double s = 0.0;
+            const int j0 = i - kl > 0 ? i - kl : 0, j1 = i + ku < n - 1 ? i + ku : n - 1;
+            for (int j = j0; j <= j1; ++j) s += ab[(size_t)j * ldab + (kl + ku + i - j)] * Y[j];
+            dy[i] = omega * (-s + r[i]) + coef[i % D] * (Y[i] - muy[i % D]);
+        }
+        for (int i = 0; i < n; ++i) {
+            if (dy[i] != dy[i]) { free(ab); free(r); free(dy); free(gv); return VCO_EARG; }  /* :165 @assert */
+            Y[i] = Y[i] + alpha * dy[i];                                      /* :168 eq. (52) */
+        }
+    }
+    free(ab); free(r); free(dy); free(gv);
+    return VCO_OK;
+}
+
+/* vc(c::TrajectoryConverter, fm) with a GV converter: src/common.jl:31-63, default epochs / alpha */
+int vco_vc_trajgv(vco_trajgv* v, const double* fm, int rows, int64_t T, int epochs, double alpha,
+                  double* out) {
+    int srows = rows - 1, Dout = (srows >> 1) + 1;
+    if (T < 1) return VCO_EARG;
+    int64_t limit = vco_traj_length(v->t);
+    int rc = VCO_OK;
+    int64_t count = 0;
+    double* conv = (double*)malloc(sizeof(double) * (size_t)(Dout - 1) * (size_t)(limit < T ? limit : T));
+    double* phrase = (double*)malloc(sizeof(double) * (size_t)srows * (size_t)(limit < T ? limit : T));
+    if (!conv || !phrase) { free(conv); free(phrase); return VCO_ENOMEM; }
+    for (;;) {
+        int64_t b = count * limit, e = (count + 1) * limit < T ? (count + 1) * limit : T;
+        int len = (int)(e - b);
+        for (int t = 0; t < len; ++t) memcpy(phrase + (size_t)t * srows, fm + (b + t) * rows + 1, sizeof(double) * srows);
+        rc = vco_trajgv_fvconvert(v, phrase, srows, len, epochs, alpha, conv);
+        if (rc != VCO_OK) break;
+        for (int t = 0; t < len; ++t)
+            memcpy(out + (b + t) * Dout + 1, conv + (size_t)t * (Dout - 1), sizeof(double) * (Dout - 1));
+        if (e == T) break;
+        ++count;
+    }
+    for (int64_t t = 0; t < T; ++t) out[t * Dout] = fm[t * rows];
+    free(conv); free(phrase);
+    return rc;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* diffgmm -- src/diffgmm.jl:9-25 ([Kobayashi 2014] eqs. 6-8), restated on the joint parameters */
+/* ------------------------------------------------------------------------------------------ */
+
+/* GMMMapParam(w, mux, muy - mux, Sxx, Sxy - Sxx, (Sxy - Sxx)', Sxx + Syy - Sxy - Syx) written back as
+ * a joint (2D, M) mean and (2D, 2D, M) covariance, so that GMMMap(w, mu', sigma') builds exactly
+ * that parameter set. */
+void vco_diffgmm(const double* mu, const double* sigma, int twoD, int M, double* mu_out, double* sigma_out) {
+    const int D = twoD / 2;
+    for (int m = 0; m < M; ++m) {
+        const double* u = mu + (size_t)m * twoD;
+        const double* S = sigma + (size_t)m * twoD * twoD;
+        double* uo = mu_out + (size_t)m * twoD;
+        double* So = sigma_out + (size_t)m * twoD * twoD;
+#define SG(a, b) S[(a) + (size_t)(b) * twoD]
+#define SO(a, b) So[(a) + (size_t)(b) * twoD]
+        for (int i = 0; i < D; ++i) { uo[i] = u[i]; uo[D + i] = u[D + i] - u[i]; }
+        for (int i = 0; i < D; ++i)
+            for (int j = 0; j < D; ++j) {
+                SO(i, j) = SG(i, j);                                   /* Sxx */
+                SO(i, D + j) = SG(i, D + j) - SG(i, j);                /* Sxy - Sxx */
+                SO(D + j, i) = SG(i, D + j) - SG(i, j);                /* (Sxy - Sxx)' */
+                SO(D + i, D + j) = SG(i, j) + SG(D + i, D + j) - SG(i, D + j) - SG(D + i, j);
+            }
+#undef SG
+#undef SO
+    }
 }
 
 /* src/common.jl:31-63 */

@@ -11,6 +11,9 @@
  *                                    (test/dtw.jl:7-19, 21-31) -> tests/golden/dtw_*.json
  *   constructW                    -- PINNED by test/trajectory_gmmmap.jl:1-34 (exact structure)
  *   GMMMap ctor / accessors       -- PINNED (shape only) by test/gmmmap.jl:1-15 on the real model
+ *   GV (gv.jl, TrajectoryGVGMMMap), diffgmm -- PARITY UNPINNED (the reference has no tests for them:
+ *                                    "TODO: tests", src/diffgmm.jl:8); checked through their defining
+ *                                    properties (tests/test_oracle_gv.py)
  *   fvconvert / vc numerics       -- PARITY UNPINNED by the reference: its tests only assert
  *                                    isfinite (test/vc.jl:26,50,72).  Julia 0.5 is not runnable in
  *                                    this image; the oracle is instead cross-checked against
@@ -73,6 +76,24 @@ int vco_vc_traj(vco_traj* t, const double* fm, int rows, int64_t T, double* out)
  * state of chunk limit `limit` per utterance, OpenMP over utterances */
 int vco_vc_traj_batch_mt(vco_gmmmap* g, int limit, const double* fm, int rows,
                          const int64_t* offsets, int64_t nseq, double* out, int nthreads);
+
+/* ---- src/gv.jl:6-21 : fvpostf!(VarianceScaling(s2), src (D,T)) in place ---- */
+void vco_variance_scaling(const double* s2, double* src, int D, int64_t T);
+
+/* ---- src/trajectory_gmmmap.jl:112-189 : TrajectoryGVGMMMap ---- */
+typedef struct vco_trajgv vco_trajgv;
+int vco_trajgv_create(vco_traj* t /*borrowed*/, const double* muv /*(Ds)*/, const double* svv /*(Ds,Ds)*/,
+                      vco_trajgv** out);
+void vco_trajgv_destroy(vco_trajgv* v);
+/* fvconvert(tgv, X (2Ds,T); epochs, alpha) -> Y (Ds,T) */
+int vco_trajgv_fvconvert(vco_trajgv* v, const double* X, int xrows, int T, int epochs, double alpha,
+                         double* Y);
+/* vc(tgv, fm (1+2Ds,T)) -> out (1+Ds,T), chunked by length(tgv.tgmm) */
+int vco_vc_trajgv(vco_trajgv* v, const double* fm, int rows, int64_t T, int epochs, double alpha,
+                  double* out);
+
+/* ---- src/diffgmm.jl:9-25 on the joint parameters: mu (2D,M), sigma (2D,2D,M) ---- */
+void vco_diffgmm(const double* mu, const double* sigma, int twoD, int M, double* mu_out, double* sigma_out);
 
 /* ---- src/dtw.jl ---- */
 int vco_dtw_create(int fstep, int bstep, vco_dtw** out);

@@ -17,6 +17,7 @@ for s in $stages; do
     dtw)       run t_dtw 600 python -m pytest tests/test_gpu_dtw.py -m gpu -q --tb=short -k "not full" ;;
     simt)      run t_gmm_simt 900 python -m pytest tests/test_gpu_gmmmap.py -m gpu -q --tb=short -k "not tcgen05 and not full" ;;
     traj_simt) run t_traj_simt 900 python -m pytest tests/test_gpu_traj.py -m gpu -q --tb=short -k "not tcgen05 and not full" ;;
+    gv)        run t_gv 600 python -m pytest tests/test_gpu_gv.py -m gpu -q --tb=short ;;
     aux)       run t_aux 300 python -m pytest tests/test_gpu_aux.py -m gpu -q --tb=short ;;
     tc)        run t_gmm_tc 600 python -m pytest tests/test_gpu_gmmmap.py -m gpu -q --tb=short -k "tcgen05" ;;
     traj_tc)   run t_traj_tc 600 python -m pytest tests/test_gpu_traj.py -m gpu -q --tb=short -k "tcgen05" ;;

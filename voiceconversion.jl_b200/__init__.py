@@ -30,7 +30,8 @@ from . import jld, shard, synth  # noqa: F401
 
 __all__ = [
     "AbstractConverter", "FrameByFrameConverter", "TrajectoryConverter", "GMMMapParam", "GMMMap",
-    "TrajectoryGMMMap", "fvconvert", "vc", "vc_batch", "ncomponents", "dim", "predict_proba",
+    "TrajectoryGMMMap", "TrajectoryGVGMMMap", "VarianceScaling", "fvpostf", "fvpostf_", "diffgmm",
+    "fvconvert", "fvconvert_gv", "vc", "vc_batch", "ncomponents", "dim", "predict_proba",
     "predict", "constructW", "push_delta", "align", "align_batch", "DTWs", "DimensionMismatch",
     "PosDefException", "SingularException", "ArgumentError", "CudaError", "VCBError",
     "set_device", "device_count", "set_kernel_variant", "launch_count",
@@ -193,6 +194,103 @@ class TrajectoryGMMMap(TrajectoryConverter):
         return self._Dy
 
 
+class TrajectoryGVGMMMap(TrajectoryConverter):
+    """``TrajectoryGVGMMMap(tgmm, mu_v, S_vv)``  (src/trajectory_gmmmap.jl:114-133): trajectory
+    conversion followed by gradient ascent on the likelihood with the global-variance term."""
+
+    def __init__(self, tgmm: TrajectoryGMMMap, mu_v, sigma_vv):
+        if not isinstance(tgmm, TrajectoryGMMMap):
+            raise ArgumentError(_lib.EARG, "TrajectoryGVGMMMap needs a TrajectoryGMMMap")
+        self.tgmm = tgmm
+        self.mu_v = _f64(mu_v)
+        self.sigma_vv = _f64(sigma_vv)
+        Ds = tgmm.dim // 2
+        if self.mu_v.shape != (Ds,) or self.sigma_vv.shape != (Ds, Ds):
+            raise DimensionMismatch(_lib.EDIM, "GV statistics must be (Ds,) and (Ds, Ds)")
+        self._h = C.c_void_p()
+        _lib.check(_lib.lib().vcb_trajgv_create(tgmm._h, _lib.ptr(self.mu_v), _lib.ptr(self.sigma_vv), C.byref(self._h)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.lib().vcb_trajgv_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def __len__(self) -> int:           # :129
+        return len(self.tgmm)
+
+    @property
+    def dim(self) -> int:               # :130
+        return self.tgmm.dim
+
+    @property
+    def ncomponents(self) -> int:       # :131
+        return self.tgmm.ncomponents
+
+    @property
+    def size(self):                     # :132 refers to an undefined variable `t` and throws in the reference
+        raise NameError("t not defined (Base.size(g::TrajectoryGVGMMMap), src/trajectory_gmmmap.jl:132)")
+
+
+class VarianceScaling(NamedTuple):
+    """``VarianceScaling(sigma2)``  (src/gv.jl:6-8)."""
+    sigma2: np.ndarray
+
+
+def fvpostf(vs: VarianceScaling, src, offsets=None):
+    """``fvpostf(vs, src)`` (src/gv.jl:17-21): per-dimension variance scaling of one (D, T) matrix,
+    of a concatenated batch with ``offsets`` (one filter per utterance), or of a frame-major CUDA
+    tensor.  Returns a filtered copy."""
+    L = _lib.lib()
+    s2 = _f64(vs.sigma2)
+    if _is_torch(src):
+        import torch
+        _check_dev_tensor(src)
+        T, D = src.shape
+        off = np.array([0, T], dtype=np.int64) if offsets is None else np.ascontiguousarray(offsets, dtype=np.int64)
+        out = torch.empty_like(src)
+        d_s2 = torch.from_numpy(s2).to(src.device)
+        _lib.check(L.vcb_variance_scaling_batch_dev(_lib.ptr(d_s2), D, _lib.ptr(src), D, _lib.ptr(off), len(off) - 1,
+                                                    _lib.ptr(out), D, _stream_ptr()))
+        return out
+    src = _f64(src)
+    D, T = src.shape
+    if s2.shape != (D,):
+        raise DimensionMismatch(_lib.EDIM, "VarianceScaling has %d entries, src has %d rows" % (s2.size, D))
+    off = np.array([0, T], dtype=np.int64) if offsets is None else np.ascontiguousarray(offsets, dtype=np.int64)
+    out = np.empty_like(src, order="F")
+    _lib.check(L.vcb_variance_scaling_batch(_lib.ptr(s2), D, _lib.ptr(src), D, _lib.ptr(off), len(off) - 1, _lib.ptr(out), D))
+    return out
+
+
+def fvpostf_(vs: VarianceScaling, src: np.ndarray, offsets=None) -> np.ndarray:
+    """``fvpostf!(vs, src)`` (src/gv.jl:10-15): in place on a column-major float64 array."""
+    src[...] = fvpostf(vs, src, offsets)
+    return src
+
+
+def diffgmm(params):
+    """``diffgmm(params::GMMMapParam)`` (src/diffgmm.jl:9-25).  Accepts a GMMMapParam (returns the
+    differential GMMMapParam, A recomputed as in the 7-argument constructor src/gmmmap.jl:23-38)
+    or a ``(weights, means, covars)`` joint triple (returns the joint triple of the differential
+    model, ready for ``GMMMap(...)``)."""
+    L = _lib.lib()
+    if isinstance(params, GMMMapParam):
+        D, M = params.mux.shape
+        mu = np.asfortranarray(np.concatenate([params.mux, params.muy], axis=0))
+        sg = np.empty((2 * D, 2 * D, M), order="F")
+        sg[:D, :D], sg[:D, D:], sg[D:, :D], sg[D:, D:] = params.Sxx, params.Sxy, params.Syx, params.Syy
+        w, mo, so = diffgmm((params.weights, mu, sg))
+        return GMMMap(w, mo, so).params
+    w, mu, sg = params[0], _f64(params[1]), _f64(params[2])
+    mo, so = np.empty_like(mu, order="F"), np.empty_like(sg, order="F")
+    _lib.check(L.vcb_diffgmm(_lib.ptr(mu), _lib.ptr(sg), mu.shape[0], mu.shape[1], _lib.ptr(mo), _lib.ptr(so)))
+    return type(params)(w, mo, so) if hasattr(params, "_fields") else (w, mo, so)
+
+
 def dim(c) -> int:
     return c.dim
 
@@ -271,7 +369,40 @@ def fvconvert(c, X, return_aux: bool = False):
         c._T = T                                   # W rebuilt for the new length (:70-72)
         c.Ey = Ey.reshape(-1, order="F")           # tgmm.Ey = vec(Ey)   (:90-91)
         return (Y, mhat, Ey) if return_aux else Y
+    if isinstance(c, TrajectoryGVGMMMap):
+        return _fvconvert_gv(c, X)
     raise TypeError("fvconvert: unsupported converter type")
+
+
+def _fvconvert_gv(c: "TrajectoryGVGMMMap", X, epochs: int = 100, alpha: float = 1.0e-5):
+    L = _lib.lib()
+    Ds = c.dim // 2
+    if _is_torch(X):
+        import torch
+        _check_dev_tensor(X)
+        T, rows = X.shape
+        off = np.array([0, T], dtype=np.int64)
+        Y = torch.empty((T, Ds), dtype=torch.float64, device=X.device)
+        _lib.check(L.vcb_trajgv_convert_batch_dev(c._h, _lib.ptr(X), rows, rows, _lib.ptr(off), 1, 0, int(epochs),
+                                                  float(alpha), _lib.ptr(Y), Ds, _stream_ptr()))
+        c.tgmm._T = T
+        return Y
+    X = _f64(X)
+    if X.ndim != 2:
+        raise ArgumentError(_lib.EARG, "fvconvert(::TrajectoryGVGMMMap, X) needs a matrix")
+    rows, T = X.shape
+    off = np.array([0, T], dtype=np.int64)
+    Y = np.empty((Ds, T), order="F")
+    _lib.check(L.vcb_trajgv_convert_batch(c._h, _lib.ptr(X), rows, rows, _lib.ptr(off), 1, 0, int(epochs), float(alpha),
+                                          _lib.ptr(Y), Ds))
+    c.tgmm._T = T
+    return Y
+
+
+def fvconvert_gv(c: "TrajectoryGVGMMMap", X, epochs: int = 100, alpha: float = 1.0e-5):
+    """``fvconvert(tgv, X; epochs=100, α=1.0e-5)`` (src/trajectory_gmmmap.jl:140-172) with its
+    keyword arguments."""
+    return _fvconvert_gv(c, X, epochs, alpha)
 
 
 # ---- vc -----------------------------------------------------------------------------------------
@@ -309,7 +440,7 @@ def vc(c, fm, out=None):
     raise TypeError("vc: unsupported converter type")
 
 
-def vc_batch(c: TrajectoryGMMMap, fms, offsets=None, _split: bool = True):
+def vc_batch(c, fms, offsets=None, _split: bool = True, epochs: int = 100, alpha: float = 1.0e-5):
     """Batch extension of ``vc(c::TrajectoryConverter, fm)``: every utterance is converted as
     ``vc(c, fm_s)`` would with the chunk limit ``len(c)`` read once (src/common.jl:43), all in one
     library call.  ``fms`` is a list of (1+2Ds, T_s) matrices, or one concatenated matrix /
@@ -321,14 +452,21 @@ def vc_batch(c: TrajectoryGMMMap, fms, offsets=None, _split: bool = True):
     L = _lib.lib()
     limit = len(c)
     Ds = c.dim // 2
+    gv = isinstance(c, TrajectoryGVGMMMap)      # vc passes no keywords: epochs = 100, alpha = 1e-5
+    if gv:
+        c, cgv = c.tgmm, c
     if _is_torch(fms):
         import torch
         _check_dev_tensor(fms)
         off = np.ascontiguousarray(offsets, dtype=np.int64)
         total, rows = fms.shape
         out = torch.empty((total, Ds + 1), dtype=torch.float64, device=fms.device)
-        _lib.check(L.vcb_traj_vc_batch_dev(c._h, _lib.ptr(fms), rows, _lib.ptr(off), len(off) - 1, limit,
-                                           _lib.ptr(out), _stream_ptr()))
+        if gv:
+            _lib.check(L.vcb_trajgv_vc_batch_dev(cgv._h, _lib.ptr(fms), rows, _lib.ptr(off), len(off) - 1, limit,
+                                                 int(epochs), float(alpha), _lib.ptr(out), _stream_ptr()))
+        else:
+            _lib.check(L.vcb_traj_vc_batch_dev(c._h, _lib.ptr(fms), rows, _lib.ptr(off), len(off) - 1, limit,
+                                               _lib.ptr(out), _stream_ptr()))
         _update_len(c, off, limit)
         return (out,) if not _split else [out[off[i]:off[i + 1]] for i in range(len(off) - 1)]
     if offsets is None:
@@ -344,7 +482,11 @@ def vc_batch(c: TrajectoryGMMMap, fms, offsets=None, _split: bool = True):
         rows = fm.shape[0]
         off = np.ascontiguousarray(offsets, dtype=np.int64)
     out = np.empty((Ds + 1, fm.shape[1]), order="F")
-    _lib.check(L.vcb_traj_vc_batch(c._h, _lib.ptr(fm), rows, _lib.ptr(off), len(off) - 1, limit, _lib.ptr(out)))
+    if gv:
+        _lib.check(L.vcb_trajgv_vc_batch(cgv._h, _lib.ptr(fm), rows, _lib.ptr(off), len(off) - 1, limit, int(epochs),
+                                         float(alpha), _lib.ptr(out)))
+    else:
+        _lib.check(L.vcb_traj_vc_batch(c._h, _lib.ptr(fm), rows, _lib.ptr(off), len(off) - 1, limit, _lib.ptr(out)))
     _update_len(c, off, limit)
     if offsets is not None and not _split:
         return (out,)

@@ -87,6 +87,15 @@ SIGNATURES = {
     "vcb_dtw_fit_batch": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "vcb_dtw_fit_batch_dev": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp]),
     "vcb_dtw_update": (_i32, [_vp, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "vcb_trajgv_create": (_i32, [_vp, _vp, _vp, C.POINTER(_vp)]),
+    "vcb_trajgv_destroy": (_i32, [_vp]),
+    "vcb_trajgv_convert_batch": (_i32, [_vp, _vp, _i32, _i64, _vp, _i64, _i32, _i32, C.c_double, _vp, _i64]),
+    "vcb_trajgv_convert_batch_dev": (_i32, [_vp, _vp, _i32, _i64, _vp, _i64, _i32, _i32, C.c_double, _vp, _i64, _vp]),
+    "vcb_trajgv_vc_batch": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, _i32, C.c_double, _vp]),
+    "vcb_trajgv_vc_batch_dev": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, _i32, C.c_double, _vp, _vp]),
+    "vcb_variance_scaling_batch": (_i32, [_vp, _i32, _vp, _i64, _vp, _i64, _vp, _i64]),
+    "vcb_variance_scaling_batch_dev": (_i32, [_vp, _i32, _vp, _i64, _vp, _i64, _vp, _i64, _vp]),
+    "vcb_diffgmm": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp]),
     "vcb_push_delta_batch": (_i32, [_vp, _i32, _vp, _i64, _vp]),
     "vcb_align_batch": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
 }

@@ -106,9 +106,11 @@ static void build_chunks(const int64_t* offsets, int64_t nseq, int chunk_limit, 
     }
 }
 
+struct GvRun { const vcb_trajgv* gv = nullptr; int epochs = 0; double alpha = 0.0; };
+
 static int32_t traj_device(const vcb_traj& t, const double* dX, int64_t ldx, const int64_t* offsets,
                            int64_t nseq, int chunk_limit, double* dY, int64_t ldy, int64_t* dmhat,
-                           double* dEy, bool copy_power, cudaStream_t st) {
+                           double* dEy, bool copy_power, cudaStream_t st, GvRun gvr = GvRun()) {
     const vcb_gmmmap& g = *t.g;
     if (nseq <= 0) return VCB_OK;
     const int64_t base = offsets[0], total = offsets[nseq] - base;
@@ -124,6 +126,13 @@ static int32_t traj_device(const vcb_traj& t, const double* dX, int64_t ldx, con
     Scratch sc(st);
     int32_t* d_mhat = nullptr;
     int64_t* d_chunks = nullptr;
+    if (gvr.gv) {
+        // var(y, 2) of a one-frame chunk is NaN in the reference, whose @assert then fires (:165)
+        for (int64_t c = 0; c < nchunks; ++c)
+            if (chunks[c + 1] - chunks[c] < 2) return fail(VCB_EARG, "GV conversion needs at least 2 frames per chunk");
+        if (!dEy) { VCB_CUDA(sc.get(&dEy, (size_t)total * g.D)); dEy -= base * g.D; }
+        if (!dmhat) { VCB_CUDA(sc.get(&dmhat, (size_t)total)); dmhat -= base; }
+    }
     VCB_CUDA(sc.get(&d_mhat, (size_t)total));
     VCB_CUDA(sc.get(&d_chunks, chunks.size()));
     VCB_CUDA(cudaMemcpyAsync(d_chunks, chunks.data(), chunks.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
@@ -132,6 +141,9 @@ static int32_t traj_device(const vcb_traj& t, const double* dX, int64_t ldx, con
     VCB_TRY(traj_solve_device(t, X0, ldx, d_mhat, d_chunks, nchunks, maxlen, total, dY + base * ldy, ldy,
                               dEy ? dEy + base * g.D : nullptr, copy_power, st));
     if (dmhat) VCB_TRY(widen_mhat(d_mhat, total, dmhat + base, st));
+    if (gvr.gv)      // src/trajectory_gmmmap.jl:150-171
+        VCB_TRY(trajgv_ascent_device(*gvr.gv, dY + base * ldy, ldy, dEy + base * g.D, dmhat + base, d_chunks, nchunks,
+                                     total, gvr.epochs, gvr.alpha, st));
     return VCB_OK;
 }
 
@@ -458,7 +470,8 @@ int32_t vcb_traj_vc_batch_dev(const vcb_traj* t, const double* dfm, int32_t rows
 }
 
 static int32_t traj_host(const vcb_traj& t, const double* X, int64_t ldx, const int64_t* offsets, int64_t nseq,
-                         int chunk_limit, double* Y, int64_t ldy, int64_t* mhat, double* Ey, bool whole_rows) {
+                         int chunk_limit, double* Y, int64_t ldy, int64_t* mhat, double* Ey, bool whole_rows,
+                         GvRun gvr = GvRun()) {
     if (nseq == 0) return VCB_OK;
     const int64_t base = offsets[0], total = offsets[nseq] - base;
     if (total <= 0) return VCB_OK;
@@ -477,7 +490,7 @@ static int32_t traj_host(const vcb_traj& t, const double* X, int64_t ldx, const 
     VCB_CUDA(cudaMemcpyAsync(dX, X + base * ldx - pre, in_elems * sizeof(double), cudaMemcpyHostToDevice, st));
     std::vector<int64_t> rel(offsets, offsets + nseq + 1);
     for (auto& o : rel) o -= base;
-    VCB_TRY(traj_device(t, dX + pre, ldx, rel.data(), nseq, chunk_limit, dY + pre, ldy, dm, dE, whole_rows, st));
+    VCB_TRY(traj_device(t, dX + pre, ldx, rel.data(), nseq, chunk_limit, dY + pre, ldy, dm, dE, whole_rows, st, gvr));
     if (whole_rows || ldy == Ds) {
         VCB_CUDA(cudaMemcpyAsync(Y + base * ldy - pre, dY, out_elems * sizeof(double), cudaMemcpyDeviceToHost, st));
     } else {
@@ -509,6 +522,153 @@ int32_t vcb_traj_vc_batch(const vcb_traj* t, const double* fm, int32_t rows, con
     if (!fm || !out) return fail(VCB_EARG, "null argument");
     VCB_TRY(use_device_of(t->g->device));
     return traj_host(*t, fm + 1, rows, offsets, nseq, chunk_limit, out + 1, t->Ds + 1, nullptr, nullptr, true);
+    VCB_GUARD_END
+}
+
+// ------------------------------------------------------------------------------------------------
+// TrajectoryGVGMMMap, VarianceScaling, diffgmm
+// ------------------------------------------------------------------------------------------------
+int32_t vcb_trajgv_create(const vcb_traj* t, const double* mu_v, const double* sigma_vv, vcb_trajgv** out) {
+    VCB_GUARD_BEGIN
+    if (!t || !mu_v || !sigma_vv || !out) return fail(VCB_EARG, "null argument");
+    *out = nullptr;
+    const int Ds = t->Ds;
+    for (int i = 0; i < Ds; ++i)      // @assert sum(mu_v .< 0) == 0   src/trajectory_gmmmap.jl:124
+        if (mu_v[i] < 0.0) return fail(VCB_EARG, "GV mean %d is negative", i + 1);
+    std::vector<double> pv(sigma_vv, sigma_vv + (size_t)Ds * Ds);
+    if (!invert_matrix(pv, Ds)) return fail(VCB_ESINGULAR, "GV covariance is singular");   // inv(S_vv)  :125
+    VCB_TRY(use_device_of(t->g->device));
+    vcb_trajgv* v = new vcb_trajgv();
+    v->t = t;
+    v->muv.assign(mu_v, mu_v + Ds);
+    v->pv = pv;
+    if (v->d_muv.upload(v->muv) != cudaSuccess || v->d_pv.upload(v->pv) != cudaSuccess) {
+        delete v;
+        return fail(VCB_ECUDA, "device upload of the GV parameters failed");
+    }
+    *out = v;
+    return VCB_OK;
+    VCB_GUARD_END
+}
+
+int32_t vcb_trajgv_destroy(vcb_trajgv* v) {
+    if (!v) return VCB_OK;
+    use_device_of(v->t->g->device);
+    delete v;
+    return VCB_OK;
+}
+
+static int32_t gv_args(const vcb_trajgv* v, int32_t epochs) {
+    if (!v) return fail(VCB_EARG, "null argument");
+    if (epochs < 0) return fail(VCB_EARG, "negative epochs");
+    return VCB_OK;
+}
+
+int32_t vcb_trajgv_convert_batch_dev(const vcb_trajgv* v, const double* dX, int32_t xrows, int64_t ldx,
+                                     const int64_t* offsets, int64_t nseq, int32_t chunk_limit, int32_t epochs,
+                                     double alpha, double* dY, int64_t ldy, void* stream) {
+    VCB_GUARD_BEGIN
+    VCB_TRY(gv_args(v, epochs));
+    VCB_TRY(traj_check(v->t, xrows, ldx, offsets, nseq));
+    if (!dX || !dY) return fail(VCB_EARG, "null argument");
+    if (ldy < v->t->Ds) return fail(VCB_EARG, "ldy < dim/2");
+    VCB_TRY(use_device_of(v->t->g->device));
+    return traj_device(*v->t, dX, ldx, offsets, nseq, chunk_limit, dY, ldy, nullptr, nullptr, false,
+                       (cudaStream_t)stream, GvRun{v, epochs, alpha});
+    VCB_GUARD_END
+}
+
+int32_t vcb_trajgv_vc_batch_dev(const vcb_trajgv* v, const double* dfm, int32_t rows, const int64_t* offsets,
+                                int64_t nseq, int32_t chunk_limit, int32_t epochs, double alpha, double* dout,
+                                void* stream) {
+    VCB_GUARD_BEGIN
+    VCB_TRY(gv_args(v, epochs));
+    VCB_TRY(traj_check(v->t, rows - 1, rows, offsets, nseq));
+    if (!dfm || !dout) return fail(VCB_EARG, "null argument");
+    VCB_TRY(use_device_of(v->t->g->device));
+    return traj_device(*v->t, dfm + 1, rows, offsets, nseq, chunk_limit, dout + 1, v->t->Ds + 1, nullptr, nullptr, true,
+                       (cudaStream_t)stream, GvRun{v, epochs, alpha});
+    VCB_GUARD_END
+}
+
+int32_t vcb_trajgv_convert_batch(const vcb_trajgv* v, const double* X, int32_t xrows, int64_t ldx,
+                                 const int64_t* offsets, int64_t nseq, int32_t chunk_limit, int32_t epochs,
+                                 double alpha, double* Y, int64_t ldy) {
+    VCB_GUARD_BEGIN
+    VCB_TRY(gv_args(v, epochs));
+    VCB_TRY(traj_check(v->t, xrows, ldx, offsets, nseq));
+    if (!X || !Y) return fail(VCB_EARG, "null argument");
+    if (ldy < v->t->Ds) return fail(VCB_EARG, "ldy < dim/2");
+    VCB_TRY(use_device_of(v->t->g->device));
+    return traj_host(*v->t, X, ldx, offsets, nseq, chunk_limit, Y, ldy, nullptr, nullptr, false, GvRun{v, epochs, alpha});
+    VCB_GUARD_END
+}
+
+int32_t vcb_trajgv_vc_batch(const vcb_trajgv* v, const double* fm, int32_t rows, const int64_t* offsets,
+                            int64_t nseq, int32_t chunk_limit, int32_t epochs, double alpha, double* out) {
+    VCB_GUARD_BEGIN
+    VCB_TRY(gv_args(v, epochs));
+    VCB_TRY(traj_check(v->t, rows - 1, rows, offsets, nseq));
+    if (!fm || !out) return fail(VCB_EARG, "null argument");
+    VCB_TRY(use_device_of(v->t->g->device));
+    return traj_host(*v->t, fm + 1, rows, offsets, nseq, chunk_limit, out + 1, v->t->Ds + 1, nullptr, nullptr, true,
+                     GvRun{v, epochs, alpha});
+    VCB_GUARD_END
+}
+
+int32_t vcb_variance_scaling_batch_dev(const double* d_sigma2, int32_t D, const double* dX, int64_t ldx,
+                                       const int64_t* offsets, int64_t nseq, double* dY, int64_t ldy, void* stream) {
+    VCB_GUARD_BEGIN
+    if (!d_sigma2 || !dX || !dY || !offsets) return fail(VCB_EARG, "null argument");
+    if (D < 1 || nseq < 0 || ldx < D || ldy < D) return fail(VCB_EARG, "bad arguments");
+    if (nseq == 0) return VCB_OK;
+    VCB_TRY(ensure_device());
+    cudaStream_t st = (cudaStream_t)stream;
+    Scratch sc(st);
+    int64_t* dOff = nullptr;
+    VCB_CUDA(sc.get(&dOff, (size_t)nseq + 1));
+    VCB_CUDA(cudaMemcpyAsync(dOff, offsets, ((size_t)nseq + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    return variance_scaling_device(d_sigma2, D, dX, ldx, dOff, nseq, dY, ldy, st);
+    VCB_GUARD_END
+}
+
+int32_t vcb_variance_scaling_batch(const double* sigma2, int32_t D, const double* X, int64_t ldx,
+                                   const int64_t* offsets, int64_t nseq, double* Y, int64_t ldy) {
+    VCB_GUARD_BEGIN
+    if (!sigma2 || !X || !Y || !offsets) return fail(VCB_EARG, "null argument");
+    if (D < 1 || nseq < 0 || ldx < D || ldy < D) return fail(VCB_EARG, "bad arguments");
+    if (nseq == 0) return VCB_OK;
+    VCB_TRY(ensure_device());
+    const int64_t base = offsets[0], total = offsets[nseq] - base;
+    if (total <= 0) return VCB_OK;
+    cudaStream_t st = nullptr;
+    Scratch sc(st);
+    double *dS = nullptr, *dI = nullptr, *dO = nullptr;
+    int64_t* dOff = nullptr;
+    VCB_CUDA(sc.get(&dS, (size_t)D));
+    VCB_CUDA(sc.get(&dI, (size_t)total * D));
+    VCB_CUDA(sc.get(&dO, (size_t)total * D));
+    VCB_CUDA(sc.get(&dOff, (size_t)nseq + 1));
+    std::vector<int64_t> rel(offsets, offsets + nseq + 1);
+    for (auto& o : rel) o -= base;
+    VCB_CUDA(cudaMemcpyAsync(dS, sigma2, (size_t)D * sizeof(double), cudaMemcpyHostToDevice, st));
+    VCB_CUDA(cudaMemcpy2DAsync(dI, D * sizeof(double), X + base * ldx, ldx * sizeof(double), D * sizeof(double), total,
+                               cudaMemcpyHostToDevice, st));
+    VCB_CUDA(cudaMemcpyAsync(dOff, rel.data(), rel.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    VCB_TRY(variance_scaling_device(dS, D, dI, D, dOff, nseq, dO, D, st));
+    VCB_CUDA(cudaMemcpy2DAsync(Y + base * ldy, ldy * sizeof(double), dO, D * sizeof(double), D * sizeof(double), total,
+                               cudaMemcpyDeviceToHost, st));
+    VCB_CUDA(cudaStreamSynchronize(st));
+    return VCB_OK;
+    VCB_GUARD_END
+}
+
+int32_t vcb_diffgmm(const double* mu, const double* sigma, int32_t twoD, int32_t M, double* mu_out, double* sigma_out) {
+    VCB_GUARD_BEGIN
+    if (!mu || !sigma || !mu_out || !sigma_out) return fail(VCB_EARG, "null argument");
+    if (twoD < 2 || (twoD & 1) || M < 1) return fail(VCB_EARG, "bad joint dimension %d or M %d", twoD, M);
+    diffgmm_params(mu, sigma, twoD, M, mu_out, sigma_out);
+    return VCB_OK;
     VCB_GUARD_END
 }
 

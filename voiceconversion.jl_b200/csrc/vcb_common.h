@@ -104,6 +104,13 @@ struct vcb_gmmmap {
     vcb_tc_pack tc;
 };
 
+struct vcb_traj;
+struct vcb_trajgv {
+    const vcb_traj* t = nullptr;      // borrowed
+    std::vector<double> muv, pv;      // GV mean (Ds), inv(S_vv) (Ds,Ds) column-major
+    vcb::DevBuf<double> d_muv, d_pv;
+};
+
 struct vcb_traj {
     const vcb_gmmmap* g = nullptr;
     int Ds = 0;                 // static dimension = dim(g)/2

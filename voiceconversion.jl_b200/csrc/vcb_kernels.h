@@ -47,6 +47,14 @@ int32_t traj_solve_device(const vcb_traj& t, const double* dX, int64_t ldx, cons
                           int64_t total_frames, double* dY, int64_t ldy, double* dEy_out,
                           bool copy_power, cudaStream_t st);
 
+// ---- GV helpers (vcb_gv.cu)
+int32_t variance_scaling_device(const double* d_s2, int D, const double* dX, int64_t ldx, const int64_t* d_off,
+                                int64_t nseq, double* dY, int64_t ldy, cudaStream_t st);
+// gradient ascent of fvconvert(tgv, X) on the solved trajectories dY (in place); d_mhat 1-based
+int32_t trajgv_ascent_device(const vcb_trajgv& v, double* dY, int64_t ldy, const double* dE, const int64_t* d_mhat,
+                             const int64_t* d_chunk_off, int64_t nchunks, int64_t total, int epochs, double alpha,
+                             cudaStream_t st);
+
 // ---- callers either side (vcb_aux.cu)
 int32_t push_delta_device(const double* d_src, int D, const int64_t* d_off, int64_t nseq,
                           int64_t total, double* d_out, cudaStream_t st);

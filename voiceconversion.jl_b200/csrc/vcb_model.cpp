@@ -50,6 +50,33 @@ static bool invert_general(std::vector<double>& a, int n) {
     return true;
 }
 
+bool invert_matrix(std::vector<double>& a, int n) { return invert_general(a, n); }
+
+// GMMMapParam(w, mux, muy - mux, Sxx, Sxy - Sxx, (Sxy - Sxx)', Sxx + Syy - Sxy - Syx)  ([Kobayashi 2014]
+// eqs. 6-8) written back as joint parameters, so that vcb_gmmmap_create builds exactly that model.
+void diffgmm_params(const double* mu, const double* sigma, int twoD, int M, double* mu_out, double* sigma_out) {
+    const int D = twoD / 2;
+    for (int m = 0; m < M; ++m) {
+        const double* u = mu + (size_t)m * twoD;
+        const double* S = sigma + (size_t)m * twoD * twoD;
+        double* uo = mu_out + (size_t)m * twoD;
+        double* So = sigma_out + (size_t)m * twoD * twoD;
+        auto s = [&](int r, int c) { return S[r + (size_t)c * twoD]; };
+        for (int i = 0; i < D; ++i) {
+            uo[i] = u[i];
+            uo[D + i] = u[D + i] - u[i];
+        }
+        for (int c = 0; c < D; ++c)
+            for (int r = 0; r < D; ++r) {
+                const double xy = s(r, D + c) - s(r, c);
+                So[r + (size_t)c * twoD] = s(r, c);
+                So[r + (size_t)(D + c) * twoD] = xy;
+                So[(D + c) + (size_t)r * twoD] = xy;
+                So[(D + r) + (size_t)(D + c) * twoD] = s(r, c) + s(D + r, D + c) - s(r, D + c) - s(D + r, c);
+            }
+    }
+}
+
 // Lower Cholesky factor of the matrix whose UPPER triangle is stored in s (Hermitian(s, :U),
 // src/gmm.jl:16).  Row-major output l[i*n + j].  Returns false if not positive definite.
 static bool cholesky_from_upper(const double* s, int n, std::vector<double>& l) {

@@ -8,6 +8,10 @@ int32_t build_gmmmap(const double* weights, const double* mu, const double* sigm
                      int swap, vcb_gmmmap& g);
 int32_t build_traj(const vcb_gmmmap& g, vcb_traj& t);
 void tf32_split(double v, float& hi, float& lo);
+// dense inverse like Julia's inv / ^-1 (false: singular); a is n x n column-major, inverted in place
+bool invert_matrix(std::vector<double>& a, int n);
+// diffgmm (src/diffgmm.jl:9-25) on the joint parameters mu (2D,M), sigma (2D,2D,M)
+void diffgmm_params(const double* mu, const double* sigma, int twoD, int M, double* mu_out, double* sigma_out);
 
 // Tile plan of the tcgen05 kernels (shared by the packer and the launcher; vcb_fbf_tc.cu).
 struct TcPlan {
