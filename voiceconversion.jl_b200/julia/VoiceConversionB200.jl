@@ -18,6 +18,7 @@ using Libdl
 import Base: length, size
 
 export FrameByFrameConverter, TrajectoryConverter, GMMMapParam, GMMMap, TrajectoryGMMMap,
+       TrajectoryGVGMMMap, VarianceScaling, fvpostf, fvpostf!, diffgmm,
        fvconvert, vc, ncomponents, dim, push_delta, align
 
 const libvcb200 = get(ENV, "LIBVCB200", joinpath(@__DIR__, "..", "libvcb200.so"))
@@ -179,6 +180,73 @@ function vc(c::TrajectoryGMMMap, fms::Vector{Matrix{Float64}})
         c.T = r == 0 ? min(limit, Tlast) : r       # length of the last chunk solved (quirk Q3)
     end
     [out[:, off[i]+1:off[i+1]] for i in 1:length(fms)]
+end
+
+# ---- TrajectoryGVGMMMap (src/trajectory_gmmmap.jl:112-189) ----------------------------------------
+mutable struct TrajectoryGVGMMMap <: TrajectoryConverter
+    tgmm::TrajectoryGMMMap
+    μᵛ::Vector{Float64}
+    Σᵛᵛ::Matrix{Float64}
+    handle::Ptr{Cvoid}
+
+    function TrajectoryGVGMMMap(tgmm::TrajectoryGMMMap, μᵛ::Vector{Float64}, Σᵛᵛ::Matrix{Float64})
+        h = Ref{Ptr{Cvoid}}(C_NULL)      # the library asserts μᵛ >= 0 (:124) and inverts Σᵛᵛ (:125)
+        check(ccall((:vcb_trajgv_create, libvcb200), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{Ptr{Cvoid}}),
+                    tgmm.handle, μᵛ, Σᵛᵛ, h))
+        t = new(tgmm, μᵛ, Σᵛᵛ, h[])
+        finalizer(x -> ccall((:vcb_trajgv_destroy, libvcb200), Int32, (Ptr{Cvoid},), x.handle), t)
+        t
+    end
+end
+
+length(t::TrajectoryGVGMMMap) = length(t.tgmm)      # :129
+dim(t::TrajectoryGVGMMMap) = dim(t.tgmm)            # :130
+ncomponents(t::TrajectoryGVGMMMap) = ncomponents(t.tgmm)
+
+function fvconvert(tgv::TrajectoryGVGMMMap, X::Matrix{Float64}; epochs::Int=100, α::Float64=1.0e-5, verbose::Bool=false)
+    rows, T = size(X)
+    Y = Matrix{Float64}(undef, rows >> 1, T)
+    check(ccall((:vcb_trajgv_convert_batch, libvcb200), Int32,
+                (Ptr{Cvoid}, Ptr{Float64}, Int32, Int64, Ptr{Int64}, Int64, Int32, Int32, Float64, Ptr{Float64}, Int64),
+                tgv.handle, X, rows, rows, Int64[0, T], 1, 0, epochs, α, Y, rows >> 1))
+    tgv.tgmm.T = T
+    Y
+end
+
+function vc(c::TrajectoryGVGMMMap, fms::Vector{Matrix{Float64}})
+    limit = length(c)
+    rows = size(fms[1], 1)
+    off = Int64[0; cumsum(size.(fms, 2))]
+    fm = length(fms) == 1 ? fms[1] : hcat(fms...)
+    out = Matrix{Float64}(undef, ((rows - 1) >> 1) + 1, size(fm, 2))
+    check(ccall((:vcb_trajgv_vc_batch, libvcb200), Int32,
+                (Ptr{Cvoid}, Ptr{Float64}, Int32, Ptr{Int64}, Int64, Int32, Int32, Float64, Ptr{Float64}),
+                c.handle, fm, rows, off, length(fms), limit, 100, 1.0e-5, out))
+    [out[:, off[i]+1:off[i+1]] for i in 1:length(fms)]
+end
+vc(c::TrajectoryGVGMMMap, fm::AbstractMatrix{Float64}) = vc(c, [Matrix{Float64}(fm)])[1]
+
+# ---- GV post filter (src/gv.jl:6-21) and differential model (src/diffgmm.jl:9-25) ----------------
+struct VarianceScaling
+    σ²::Vector{Float64}
+end
+
+function fvpostf!(vs::VarianceScaling, src::Matrix{Float64})
+    D, T = size(src)
+    check(ccall((:vcb_variance_scaling_batch, libvcb200), Int32,
+                (Ptr{Float64}, Int32, Ptr{Float64}, Int64, Ptr{Int64}, Int64, Ptr{Float64}, Int64),
+                vs.σ², D, src, D, Int64[0, T], 1, src, D))
+    src
+end
+fvpostf(vs::VarianceScaling, src::AbstractMatrix) = fvpostf!(vs, Matrix{Float64}(copy(src)))
+
+# joint (μ, Σ) of the differential model; GMMMap(weights, diffgmm(μ, Σ)...) is the reference's
+# GMMMapParam returned by diffgmm(params)
+function diffgmm(μ::Matrix{Float64}, Σ::Array{Float64,3})
+    μd, Σd = similar(μ), similar(Σ)
+    check(ccall((:vcb_diffgmm, libvcb200), Int32, (Ptr{Float64}, Ptr{Float64}, Int32, Int32, Ptr{Float64}, Ptr{Float64}),
+                μ, Σ, size(μ, 1), size(μ, 2), μd, Σd))
+    μd, Σd
 end
 
 # ---- DTWs (src/dtw.jl) ------------------------------------------------------------------------------
