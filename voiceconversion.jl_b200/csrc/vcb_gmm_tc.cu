@@ -43,9 +43,18 @@ constexpr int kTileM = 128;
 // TMEM, so the chunk rate is (t_mma + t_epilogue + hand-off latency) / 2: halving the epilogue's
 // per-chunk latency (a ~450-cycle dependent chain per mixture) is what raises it.  The groups'
 // partial soft-max states merge through shared memory at the end of a tile.
-constexpr int kEpiGroups = 2;
+#ifndef VCB_EPI_GROUPS
+#define VCB_EPI_GROUPS 2
+#endif
+constexpr int kEpiGroups = VCB_EPI_GROUPS;
+constexpr bool kEpiPairs = kEpiGroups < 4;   // a group reduces two mixtures at a time
 constexpr int kProducerWarp = 4 * kEpiGroups, kMmaWarp = kProducerWarp + 1, kLoaderWarp0 = kProducerWarp + 2;
-constexpr int kThreads = (kLoaderWarp0 + 2) * 32;
+#ifndef VCB_LOADER_WARPS
+#define VCB_LOADER_WARPS 2
+#endif
+constexpr int kLoaderWarps = VCB_LOADER_WARPS;      // A loaders / result storers: 128 / (32 kLoaderWarps) rows per thread
+constexpr int kLoaderThreads = 32 * kLoaderWarps;
+constexpr int kThreads = (kLoaderWarp0 + kLoaderWarps) * 32;
 constexpr int kMaxStages = 4;
 constexpr size_t kBarBytes = 1024;
 
@@ -59,6 +68,9 @@ struct TcParams {
     int64_t ntiles;
     double* Y; int64_t ldy; int copy_power;
     int32_t* mhat; int* flag_count; int64_t* flag_list;
+    int xtma;     // 1: whole input tiles are staged in shared memory by one bulk copy (xoff = doubles before X it starts at)
+    int xoff;
+    int xslack;   // rows at the end of the matrix that must not be staged (their padding may lie outside the buffer)
     int cluster;  // CTAs per cluster sharing the B operand stream by TMA multicast (1 or 2)
     long long* prof;   // VCB_TC_DEBUG=9: per-role wait/work cycle counters of CTA 0
     int debug;   // timing experiments only (VCB_TC_DEBUG): 1 = B loads shrunk to 16 B, 2 = one k-step of MMAs,
@@ -213,7 +225,7 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ float to_tf32(float v) {
+[[maybe_unused]] __device__ __forceinline__ float to_tf32(float v) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
     return __uint_as_float(r);
@@ -281,8 +293,12 @@ gmm_tc_kernel(const TcParams p) {
     auto b_empty = [&](int i) { return bar0 + 8u * (8 + kMaxStages + i); };
     const uint32_t part_full = bar0 + 8u * (8 + 2 * kMaxStages);
     const uint32_t part_empty = bar0 + 8u * (9 + 2 * kMaxStages);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * kMaxStages);
+    const uint32_t out_full = bar0 + 8u * (10 + 2 * kMaxStages);
+    const uint32_t x_full = bar0 + 8u * (11 + 2 * kMaxStages);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12 + 2 * kMaxStages);
     float* part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes);  // [PART_ROWS][128]
+    // raw Float64 input tile (conversion only, p.xtma): kTileM * ldx doubles behind the merge buffer
+    double* xraw = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(part) + (size_t)(CONVERT ? DP + 2 : 4) * 128 * sizeof(float));
     // column constants of the A operand: xbar[k] for data columns, -1 for the two ones columns, 0 for
     // padding, so that every entry is x[k] - colc[k] without branches (x = 0 outside the data)
     double* colc = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(bars) + 192);   // [KP] <= 104 doubles
@@ -291,14 +307,16 @@ gmm_tc_kernel(const TcParams p) {
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(a_full(i), 64);
+            mbar_init(a_full(i), kLoaderThreads);
             mbar_init(a_empty(i), 1);
             mbar_init(acc_full(i), 1);
-            mbar_init(acc_empty(i), 128 * kEpiGroups);
+            mbar_init(acc_empty(i), 4 * kEpiGroups);
         }
         for (int i = 0; i < kMaxStages; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), (uint32_t)p.cluster); }
         mbar_init(part_full, 128);
-        mbar_init(part_empty, 128);
+        mbar_init(part_empty, CONVERT ? kLoaderWarps : 128);   // conversion: released by the two storing warps
+        mbar_init(out_full, 4);
+        mbar_init(x_full, 1);
         fence_barrier_init();
     }
     if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -405,29 +423,81 @@ gmm_tc_kernel(const TcParams p) {
         const int row0 = threadIdx.x - kLoaderWarp0 * 32;
         long long w_load = 0;
         const long long t_begin = clock64();
+        // These warps also write the converted tile to global memory: the merging epilogue group
+        // leaves the normalised fp32 result in shared memory and goes straight back to draining
+        // accumulators (a row-per-thread store from the epilogue cost ~5 k cycles per tile during
+        // which the MMA pipe ran dry); from here the store is coalesced and off the critical path.
+        long long w_of = 0, w_st = 0;
+        auto store_tile = [&](int64_t tls) {
+            TIMED_WAIT_SLEEP(out_full, (uint32_t)(tls & 1), w_of);
+            const long long ts0 = p.prof ? clock64() : 0;
+            const int64_t t0 = (blockIdx.x + tls * gridDim.x) * kTileM;
+            {
+                constexpr int dR = kLoaderThreads / DP, dC = kLoaderThreads % DP;
+                int rr = row0 / DP, cc = row0 % DP;
+                constexpr int NE = kTileM * DP / kLoaderThreads;     // exact: kTileM is a multiple of kLoaderThreads
+                static_assert(kTileM % kLoaderThreads == 0, "store loop assumes an exact split");
+#pragma unroll 8
+                for (int i = 0; i < NE; ++i) {
+                    const int64_t t = t0 + rr;
+                    const float f = part[rr * (DP + 1) + cc];
+                    if (t < p.T && cc < p.D) p.Y[t * p.ldy + cc] = (double)f;
+                    rr += dR; cc += dC;
+                    if (cc >= DP) { cc -= DP; ++rr; }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(part_empty);
+            if (p.prof) w_st += clock64() - ts0;
+        };
+        // Input staging (p.xtma): a full tile of frames is one contiguous block of the caller's
+        // matrix, fetched by a single bulk copy one tile ahead; the conversion below then reads it
+        // from shared memory instead of issuing 25 strided global loads per row.
+        const uint32_t x_bytes = (uint32_t)(kTileM * p.ldx * sizeof(double));
+        auto tile_is_staged = [&](int64_t tli) {
+            const int64_t tile_i = blockIdx.x + tli * gridDim.x;
+            return p.xtma && tli < my_tiles && (tile_i + 1) * kTileM <= p.T - p.xslack;
+        };
+        auto stage_tile = [&](int64_t tli) {      // one thread
+            const int64_t tile_i = blockIdx.x + tli * gridDim.x;
+            mbar_expect_tx(x_full, x_bytes);
+            bulk_g2s(smem_u32(xraw), p.X - p.xoff + tile_i * kTileM * p.ldx, x_bytes, x_full);
+        };
+        if (CONVERT && row0 == 0 && tile_is_staged(0)) stage_tile(0);
+        uint32_t xph = 0;
         for (int64_t tl = 0; tl < my_tiles; ++tl) {
             const int ab = (int)(tl % AB);
             const uint32_t aph = (uint32_t)((tl / AB) & 1);
             const int64_t tile = blockIdx.x + tl * gridDim.x;
             TIMED_WAIT_SLEEP(a_empty(ab), aph ^ 1, w_load);
+            const bool staged = CONVERT && tile_is_staged(tl);
+            if (staged) { mbar_wait_sleep(x_full, xph); xph ^= 1; }
             uint8_t* hi = a_smem + (size_t)ab * a_bytes;
             uint8_t* lo = hi + a_half;
+            constexpr int RPT = kTileM / kLoaderThreads;      // rows per thread
+            // all loads of (up to 32 columns of) every row of this thread are issued before any is
+            // used: the frames stream from HBM, so memory-level parallelism is what keeps this role
+            // off the critical path
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int row = row0 + 64 * h;
-                const uint32_t row_off = (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
-                const int64_t t = tile * kTileM + row;
-                const bool live = t < p.T && p.debug != 5;
-                const double* x = p.X + (live ? t : 0) * p.ldx;
-                // all loads of (up to 32 columns of) the row are issued before any is used: the
-                // frames stream from HBM, so memory-level parallelism is what keeps this role off
-                // the critical path
+            for (int k0 = 0; k0 < DP + 8; k0 += 32) {
+                constexpr int CW = (DP + 8 < 32) ? DP + 8 : 32;
+                double xv[RPT][CW];
 #pragma unroll
-                for (int k0 = 0; k0 < DP + 8; k0 += 32) {
-                    constexpr int CW = (DP + 8 < 32) ? DP + 8 : 32;
-                    double xv[CW];
+                for (int h = 0; h < RPT; ++h) {
+                    const int64_t t = tile * kTileM + row0 + kLoaderThreads * h;
+                    const bool live = t < p.T && p.debug != 5;
+                    const double* x = staged ? xraw + (size_t)(row0 + kLoaderThreads * h) * p.ldx + p.xoff
+                                             : p.X + (live ? t : 0) * p.ldx;
 #pragma unroll
-                    for (int j = 0; j < CW; ++j) xv[j] = (live && k0 + j < p.D) ? x[k0 + j] : 0.0;
+                    for (int j = 0; j < CW; ++j) xv[h][j] = (live && k0 + j < p.D) ? x[k0 + j] : 0.0;
+                    // the power / c0 column in front of the frame passes through (src/common.jl:23);
+                    // copied here because a staged tile already holds it
+                    if (CONVERT && k0 == 0 && p.copy_power && live) p.Y[t * p.ldy - 1] = (staged && p.xoff) ? x[-1] : p.X[t * p.ldx - 1];
+                }
+#pragma unroll
+                for (int h = 0; h < RPT; ++h) {
+                    const int row = row0 + kLoaderThreads * h;
+                    const uint32_t row_off = (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
 #pragma unroll
                     for (int j4 = 0; j4 < CW; j4 += 4) {
                         if (k0 + j4 < KP) {
@@ -436,10 +506,13 @@ gmm_tc_kernel(const TcParams p) {
                             float* lp = &lv.x;
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const double v = xv[j4 + j] - colc[k0 + j4 + j];
-                                const float fh = to_tf32((float)v);
-                                hp[j] = fh;
-                                lp[j] = to_tf32((float)(v - (double)fh));
+                                // hi = v truncated to tf32's 10 mantissa bits (a mask on the Float64
+                                // bits, exact in fp32), lo = the remainder; the tensor core reads the
+                                // top 10 mantissa bits of lo, so hi + lo carries >= 21 bits of v
+                                const double v = xv[h][j4 + j] - colc[k0 + j4 + j];
+                                const double vh = __longlong_as_double(__double_as_longlong(v) & 0xFFFFFC0000000000ll);
+                                hp[j] = (float)vh;
+                                lp[j] = (float)(v - vh);
                             }
                             const uint32_t off = (uint32_t)((k0 + j4) >> 2) * (kTileM * 16u) + row_off;
                             *reinterpret_cast<float4*>(hi + off) = hv;
@@ -450,8 +523,15 @@ gmm_tc_kernel(const TcParams p) {
             }
             fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
             mbar_arrive(a_full(ab));
+            if (CONVERT && p.xtma) {
+                // every loader thread has consumed the staged tile: refill the buffer for the next one
+                asm volatile("bar.sync 2, %0;" ::"n"(kLoaderThreads) : "memory");
+                if (row0 == 0 && tile_is_staged(tl + 1)) stage_tile(tl + 1);
+            }
+            if (CONVERT && tl >= 1) store_tile(tl - 1);
         }
-        if (p.prof && blockIdx.x == 0 && row0 == 0) { p.prof[12] = w_load; p.prof[13] = clock64() - t_begin; }
+        if (CONVERT) store_tile(my_tiles - 1);
+        if (p.prof && blockIdx.x == 0 && row0 == 0) { p.prof[12] = w_load; p.prof[13] = clock64() - t_begin; p.prof[18] = w_of; p.prof[19] = w_st; }
     } else {
         // ======================= epilogue (warps 0-7; thread = frame = TMEM lane) =======================
         const int group = warp >> 2;          // with two groups: the accumulator stage this group drains
@@ -459,7 +539,7 @@ gmm_tc_kernel(const TcParams p) {
         const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
         constexpr int LOADW = (ROWS <= 64) ? ROWS : 32;   // TMEM columns fetched per wait
         int64_t it = 0;
-        long long w_full = 0, w_part = 0, w_ld = 0;
+        long long w_full = 0, w_part = 0, w_ld = 0, w_rel = 0, w_cmp = 0;
         const long long t_begin = clock64();
         for (int64_t tl = 0; tl < my_tiles; ++tl) {
             const int64_t tile = blockIdx.x + tl * gridDim.x;
@@ -471,6 +551,13 @@ gmm_tc_kernel(const TcParams p) {
 #pragma unroll
                 for (int r = 0; r < DP; ++r) y[r] = 0.f;
             }
+            // one arrival per warp: 256 per-thread arrivals on one mbarrier serialise in the shared-
+            // memory atomic unit and sat on the hand-off path of every chunk
+            auto release_stage = [&](int acc) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty(acc));
+            };
             for (int c = 0; c < NCH; ++c, ++it) {
                 const int acc = (int)(it & 1);
                 const uint32_t accph = (uint32_t)((it >> 1) & 1);
@@ -534,25 +621,26 @@ gmm_tc_kernel(const TcParams p) {
                     constexpr int GS = kEpiGroups;
                     float v0[LOADW], v1[LOADW];
                     bool released = false;
-                    for (int g = group; g < p.G; g += 2 * GS) {
-                        const bool two = g + GS < p.G;
+                    for (int g = group; g < p.G; g += (kEpiPairs ? 2 : 1) * GS) {
+                        const bool two = kEpiPairs && g + GS < p.G;
                         const float cma = cst_c[g], cmb = two ? cst_c[g + GS] : -INFINITY;   // in flight under the TMEM loads
                         const long long tl0 = p.prof ? clock64() : 0;
                         fetch(v0, g);
                         if (two) fetch(v1, g + GS);
                         tmem_ld_wait();
                         if (p.prof) w_ld += clock64() - tl0;
-                        if (g + 2 * GS >= p.G) {
+                        if (g + (kEpiPairs ? 2 : 1) * GS >= p.G) {
                             // this group's last columns of the stage are in registers: hand the
                             // accumulator back before reducing them, so the stage is held for the
                             // TMEM read only and the MMA of chunk c+2 overlaps this arithmetic
-                            tc_fence_before();
-                            mbar_arrive(acc_empty(acc));
+                            release_stage(acc);
                             released = true;
                         }
+                        const long long tc0 = p.prof ? clock64() : 0;
                         reduce2(v0, v1, g, two, cma, cmb);
+                        if (p.prof) w_cmp += clock64() - tc0;
                     }
-                    if (!released) { tc_fence_before(); mbar_arrive(acc_empty(acc)); }
+                    if (!released) release_stage(acc);
                     continue;
                 } else {
                 for (int g = group; g < p.G; g += kEpiGroups) {
@@ -601,8 +689,7 @@ gmm_tc_kernel(const TcParams p) {
                     }
                 }
                 }
-                tc_fence_before();
-                mbar_arrive(acc_empty(acc));
+                release_stage(acc);
             }
             // ---- merge the two groups' partial states of this tile (group 1 -> smem -> group 0)
             const uint32_t pph = (uint32_t)(tl & 1);
@@ -622,6 +709,7 @@ gmm_tc_kernel(const TcParams p) {
                 }
                 mbar_arrive(part_full);
             } else {
+                const long long ts0 = p.prof ? clock64() : 0;
                 if (kEpiGroups == 2) TIMED_WAIT(part_full, pph, w_part);
                 const float mxb = (kEpiGroups == 2) ? part[0 * 128 + row] : -INFINITY;
                 if (CONVERT) {
@@ -630,13 +718,17 @@ gmm_tc_kernel(const TcParams p) {
                     const float fb = (mxb == -INFINITY) ? 0.f : __expf(mxb - m2);
                     const float sumb = (kEpiGroups == 2) ? part[1 * 128 + row] : 0.f;
                     const float inv = 1.0f / (sum * fa + sumb * fb);
-                    if (t < p.T) {
-                        double* yo = p.Y + t * p.ldy;
+                    float fin[DP];
 #pragma unroll
-                        for (int r = 0; r < DP; ++r)
-                            if (r < p.D) yo[r] = (double)((y[r] * fa + ((kEpiGroups == 2) ? part[(2 + r) * 128 + row] : 0.f) * fb) * inv);
-                        if (p.copy_power) yo[-1] = p.X[t * p.ldx - 1];  // src/common.jl:23
-                    }
+                    for (int r = 0; r < DP; ++r)
+                        fin[r] = (y[r] * fa + ((kEpiGroups == 2) ? part[(2 + r) * 128 + row] : 0.f) * fb) * inv;
+                    // every thread of this group has read its partial: the buffer becomes the
+                    // tile's result [row][DP + 1] for the storing warps
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+                    for (int r = 0; r < DP; ++r) part[row * (DP + 1) + r] = fin[r];
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(out_full);
                 } else {
                     const float secb = (kEpiGroups == 2) ? part[1 * 128 + row] : -INFINITY, qb = (kEpiGroups == 2) ? part[2 * 128 + row] : 0.f;
                     const int bestb = (kEpiGroups == 2) ? __float_as_int(part[3 * 128 + row]) : 0x7FFFFFFF;
@@ -654,13 +746,15 @@ gmm_tc_kernel(const TcParams p) {
                         }
                     }
                 }
-                if (kEpiGroups == 2) mbar_arrive(part_empty);
+                if (kEpiGroups == 2 && !CONVERT) mbar_arrive(part_empty);
+                if (p.prof) w_rel += clock64() - ts0;     // (profiling: tile-end merge + store)
             }
         }
         if (p.prof && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 128)) {
             const int o = threadIdx.x == 0 ? 6 : 9;
             p.prof[o] = w_full; p.prof[o + 1] = w_part; p.prof[o + 2] = clock64() - t_begin;
             p.prof[threadIdx.x == 0 ? 14 : 15] = w_ld;
+            if (threadIdx.x == 0) { p.prof[16] = w_rel; p.prof[17] = w_cmp; }
         }
     }
 
@@ -699,14 +793,14 @@ int32_t launch_tc(const TcParams& p_in, size_t smem, cudaStream_t st) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     long long* d_prof = nullptr;
-    if (p.debug == 9) { cudaMalloc((void**)&d_prof, 16 * sizeof(long long)); cudaMemset(d_prof, 0, 16 * sizeof(long long)); p.prof = d_prof; }
+    if (p.debug == 9) { cudaMalloc((void**)&d_prof, 24 * sizeof(long long)); cudaMemset(d_prof, 0, 24 * sizeof(long long)); p.prof = d_prof; }
     VCB_CUDA(cudaLaunchKernelEx(&cfg, k, p));
     if (d_prof) {
-        long long h[16];
+        long long h[24];
         cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
         cudaFree(d_prof);
-        fprintf(stderr, "[tc prof CTA0] producer: wait b_empty %lld of %lld | mma: wait a_full %lld b_full %lld acc_empty %lld of %lld | epi0: wait acc_full %lld part %lld of %lld | epi1: wait acc_full %lld part %lld of %lld | loader: wait a_empty %lld of %lld | tmem ld epi0 %lld epi1 %lld\n",
-                h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11], h[12], h[13], h[14], h[15]);
+        fprintf(stderr, "[tc prof CTA0] producer: wait b_empty %lld of %lld | mma: wait a_full %lld b_full %lld acc_empty %lld of %lld | epi0: wait acc_full %lld part %lld of %lld | epi1: wait acc_full %lld part %lld of %lld | loader: wait a_empty %lld of %lld | tmem ld epi0 %lld epi1 %lld | epi0 tile-end %lld reduce %lld | storer: wait out_full %lld store %lld\n",
+                h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11], h[12], h[13], h[14], h[15], h[16], h[17], h[18], h[19]);
     }
     count_launch();
     VCB_CUDA(cudaGetLastError());
@@ -747,7 +841,9 @@ TcPlan tc_plan(int M, int KP, int rows_per_mixture, int part_rows) {
     // B200 (tools/micro/umma_bench.cu): one thread issues a tcgen05.mma every ~84 cycles at best,
     // an M=128 x N x K=8 tf32 MMA executes in ~N/2 + 11 cycles.
     TcPlan best;
-    const size_t extra = kBarBytes + (size_t)part_rows * 128 * sizeof(float);
+    // conversion (part_rows > 4): room for one raw Float64 input tile of up to DP + 1 columns
+    const size_t xraw_bytes = part_rows > 4 ? (size_t)kTileM * (part_rows - 1) * sizeof(double) : 0;
+    const size_t extra = kBarBytes + (size_t)part_rows * 128 * sizeof(float) + xraw_bytes;
     const int gmax = 256 / rows_per_mixture;
     if (gmax < 1) return best;
     const int ksteps = KP / 8;
@@ -789,6 +885,20 @@ static void fill_common(const vcb_gmmmap& g, const double* dX, int64_t T, int64_
     p.D = g.D; p.KP = g.tc.KP; p.G = plan.G; p.N = plan.N;
     p.NCH = convert ? g.tc.NCHC : g.tc.NCHW;
     p.stages = plan.stages; p.abufs = plan.abufs;
+    p.xtma = 0; p.xoff = 0; p.xslack = 0;
+    if (convert && ldx <= g.DP + 1) {
+        // bulk copies need 16-byte aligned global addresses; in vc() layout X = fm + 1 is odd-aligned
+        // and the power column in front of it belongs to the same matrix, so start one double early
+        const bool odd = (reinterpret_cast<uintptr_t>(dX) >> 3) & 1;
+        if ((reinterpret_cast<uintptr_t>(dX) & 7) == 0 && (!odd || ldx == g.D + 1)) {
+            static const bool off = [] { const char* e = getenv("VCB_TC_XTMA"); return e && e[0] == '0'; }();
+            p.xtma = off ? 0 : 1;
+            p.xoff = odd ? 1 : 0;
+            p.xslack = (ldx == g.D + p.xoff) ? 0 : 1;
+        }
+    }
+    static const int force_stages = [] { const char* e = getenv("VCB_TC_STAGES"); return e ? atoi(e) : 0; }();
+    if (force_stages >= 1 && force_stages < p.stages) p.stages = force_stages;     // experiments only
     p.ntiles = (T + kTileM - 1) / kTileM;
     static const int dbg = [] { const char* e = getenv("VCB_TC_DEBUG"); return e ? atoi(e) : 0; }();
     p.debug = dbg;
