@@ -270,7 +270,9 @@ template <int DP, bool CONVERT>
 __global__ void __launch_bounds__(kThreads, 1)
 gmm_tc_kernel(const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: provably warp-uniform, so the role branches are uniform branches
+    // and the issuing warp's descriptors can live in uniform registers (CUTLASS canonical_warp_idx_sync)
+    const int warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int KP = p.KP, N = p.N, NCH = p.NCH, S = p.stages, AB = p.abufs;
     constexpr int ROWS = CONVERT ? 2 * DP : DP;  // TMEM columns per mixture
 
@@ -389,24 +391,23 @@ gmm_tc_kernel(const TcParams p) {
                     uint64_t dal = make_desc(a_hi + a_half, kTileM * 16u, 128u);
                     uint64_t dbh = make_desc(b_hi, (uint32_t)N * 16u, 128u);
                     uint64_t dbl = make_desc(b_hi + b_half, (uint32_t)N * 16u, 128u);
+                    // one elected region per chunk: the descriptor bases move to uniform registers
+                    // once and the k-step offsets are uniform adds (an elected region per k-step
+                    // re-moved all twelve operands each time, ~40 issue cycles per MMA)
                     if (elect_one()) {
                         umma_tf32(d_tmem, dal, dbh, idesc, 0u);  // small terms first; first MMA overwrites
                         umma_tf32(d_tmem, dah, dbl, idesc, 1u);
                         umma_tf32(d_tmem, dah, dbh, idesc, 1u);
-                    }
-                    for (int kk = 1; kk < ksteps; ++kk) {
-                        dah += astep; dal += astep; dbh += bstep; dbl += bstep;
-                        if (elect_one()) {
+                        for (int kk = 1; kk < ksteps; ++kk) {
+                            dah += astep; dal += astep; dbh += bstep; dbl += bstep;
                             umma_tf32(d_tmem, dal, dbh, idesc, 1u);
                             umma_tf32(d_tmem, dah, dbl, idesc, 1u);
                             umma_tf32(d_tmem, dah, dbh, idesc, 1u);
                         }
-                    }
-                    if (p.koff) {   // offset k-step: ones (exact in tf32) x [o_hi, o_lo]: one pass is exact
-                        dah += astep; dbh += bstep;
-                        if (elect_one()) umma_tf32(d_tmem, dah, dbh, idesc, 1u);
-                    }
-                    if (elect_one()) {
+                        if (p.koff) {   // offset k-step: ones (exact in tf32) x [o_hi, o_lo]: one pass is exact
+                            dah += astep; dbh += bstep;
+                            umma_tf32(d_tmem, dah, dbh, idesc, 1u);
+                        }
                         // B stage may be refilled once these MMAs retire -- in every CTA of the cluster
                         if (p.cluster > 1) umma_commit_mcast(b_empty(s), cmask);
                         else umma_commit(b_empty(s));
