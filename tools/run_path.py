@@ -23,6 +23,15 @@ if which == "traj":
     d = torch.from_numpy(np.ascontiguousarray(fm.T)).cuda()
     ms = timeit(lambda: vcb.vc_batch(t, d, off, _split=False))
     print(f"traj C2 n={n} limit={limit}: {ms:.3f} ms  {n*500/ms*1e3:.3e} frames/s")
+elif which == "gv":
+    n = int(os.environ.get("N_UTT", 1000)); limit = int(os.environ.get("LIMIT", 500)); ep = int(os.environ.get("EPOCHS", 100))
+    gm, fm, off = vcb.synth.config_c2(n, 500)
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((24, 24))
+    tg = vcb.TrajectoryGVGMMMap(vcb.TrajectoryGMMMap(vcb.GMMMap(*gm), limit), rng.uniform(0.2, 1.0, 24), a @ a.T + 24 * np.eye(24))
+    d = torch.from_numpy(np.ascontiguousarray(fm.T)).cuda()
+    ms = timeit(lambda: vcb.vc_batch(tg, d, off, _split=False, epochs=ep))
+    print(f"traj+GV C2 n={n} limit={limit} epochs={ep}: {ms:.3f} ms  {n*500/ms*1e3:.3e} frames/s")
 elif which == "dtw":
     tm, to, sq, so = vcb.synth.config_c3(int(os.environ.get("N_PAIRS", 1000)))
     a = torch.from_numpy(np.ascontiguousarray(tm.T)).cuda(); b = torch.from_numpy(np.ascontiguousarray(sq.T)).cuda()
