@@ -79,6 +79,9 @@ struct vcb_tc_pack {
     int NCHC = 0, NCHW = 0; // number of chunks = ceil(M / G)
     vcb::DevBuf<float> Bc;  // [NCHC][2 (hi,lo)][image NC x KP]   whitening + regression rows
     vcb::DevBuf<float> Bw;  // [NCHW][2 (hi,lo)][image NW x KP]   whitening rows only
+    // the same operands split by row halves for CTA-pair MMAs (cta_group::2): per chunk
+    // [CTA rank 0: hi, lo images of rows 0..N/2) | [rank 1: hi, lo of rows N/2..N)]
+    vcb::DevBuf<float> Bc2, Bw2;
     vcb::DevBuf<float> cst; // c_m = log w - (D log 2pi + logdet)/2, padded with -inf
 };
 

@@ -62,6 +62,7 @@ struct TcParams {
     const double* X; int64_t T; int64_t ldx;
     const double* xbar;
     const float* B;        // [NCH][2][N*KP] operand images (hi, lo)
+    const float* Bpair;    // the same, split by row halves for CTA-pair MMAs
     const float* cst;      // [NCH*G]
     int D, KP, G, NCH, N, stages, abufs;
     int c1, koff;          // ones columns (c1, c1+1); koff = 1: they form a last k-step that needs one MMA
@@ -71,6 +72,7 @@ struct TcParams {
     int xtma;     // 1: whole input tiles are staged in shared memory by one bulk copy (xoff = doubles before X it starts at)
     int xoff;
     int xslack;   // rows at the end of the matrix that must not be staged (their padding may lie outside the buffer)
+    int pair;     // 1: CTA-pair MMAs (cta_group::2, M = 256): rank 0 issues for both SMs, each CTA holds N/2 rows of B
     int cluster;  // CTAs per cluster sharing the B operand stream by TMA multicast (1 or 2)
     long long* prof;   // VCB_TC_DEBUG=9: per-role wait/work cycle counters of CTA 0
     int debug;   // timing experiments only (VCB_TC_DEBUG): 1 = B loads shrunk to 16 B, 2 = one k-step of MMAs,
@@ -140,6 +142,54 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// ---- CTA-pair (cta_group::2) variants and cluster-scope barrier operations
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+// arrive on a barrier of another CTA of the cluster (address from mapa_rank)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// same without release semantics: for hand-offs that order tensor-memory accesses only (the
+// tcgen05 fences do that); a cluster-scope release costs several hundred cycles per arrival
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait on a local barrier that receives arrivals from the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP_C:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE_C;\n"
+        "bra WAIT_LOOP_C;\n"
+        "DONE_C:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem, 128 rows per CTA] * B[smem, N/2 rows per CTA], M = 256
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
@@ -273,13 +323,18 @@ gmm_tc_kernel(const TcParams p) {
     // warp index through a shuffle: provably warp-uniform, so the role branches are uniform branches
     // and the issuing warp's descriptors can live in uniform registers (CUTLASS canonical_warp_idx_sync)
     const int warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-    const int KP = p.KP, N = p.N, NCH = p.NCH, S = p.stages, AB = p.abufs;
+    const int KP = p.KP, N = p.N, NCH = p.NCH, AB = p.abufs;
+    const bool pair = p.pair != 0;
+    const uint32_t crank = (p.cluster > 1) ? cluster_ctarank() : 0u;
+    const bool leader = crank == 0;
+    const int NB = pair ? N / 2 : N;                 // rows of B held by this CTA
+    const int S = pair ? min(kMaxStages, 2 * p.stages) : p.stages;   // half-size stages in pair mode
     constexpr int ROWS = CONVERT ? 2 * DP : DP;  // TMEM columns per mixture
 
     // ---- shared memory carve-up
     const uint32_t a_half = kTileM * KP * 4;      // one of hi / lo
     const uint32_t a_bytes = 2 * a_half;
-    const uint32_t b_half = (uint32_t)N * KP * 4;
+    const uint32_t b_half = (uint32_t)NB * KP * 4;
     const uint32_t b_bytes = 2 * b_half;
     uint8_t* a_smem = smem_raw;
     uint8_t* b_smem = a_smem + (size_t)AB * a_bytes;
@@ -309,19 +364,22 @@ gmm_tc_kernel(const TcParams p) {
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(a_full(i), kLoaderThreads);
+            mbar_init(a_full(i), pair ? 2 * kLoaderThreads : kLoaderThreads);    // pair: both CTAs' loaders arrive at rank 0
             mbar_init(a_empty(i), 1);
             mbar_init(acc_full(i), 1);
-            mbar_init(acc_empty(i), 4 * kEpiGroups);
+            mbar_init(acc_empty(i), (pair ? 8 : 4) * kEpiGroups);
         }
-        for (int i = 0; i < kMaxStages; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), (uint32_t)p.cluster); }
+        for (int i = 0; i < kMaxStages; ++i) {
+            mbar_init(b_full(i), (pair && leader) ? 2 : 1);      // pair: own expect_tx + the peer's relay
+            mbar_init(b_empty(i), pair ? 1u : (uint32_t)p.cluster);
+        }
         mbar_init(part_full, 128);
         mbar_init(part_empty, CONVERT ? kLoaderWarps : 128);   // conversion: released by the two storing warps
         mbar_init(out_full, 4);
         mbar_init(x_full, 1);
         fence_barrier_init();
     }
-    if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (warp == kMmaWarp) { if (pair) tmem_alloc2(smem_u32(tmem_slot), 512); else tmem_alloc(smem_u32(tmem_slot), 512); }
     tc_fence_before();
     __syncthreads();
     if (p.cluster > 1) cluster_sync_all();   // peers' barriers are initialised before any remote arrive / multicast
@@ -348,7 +406,10 @@ gmm_tc_kernel(const TcParams p) {
                 mbar_expect_tx(b_full(s), nbytes);
                 const uint32_t dst = smem_u32(b_smem + (size_t)s * b_bytes);
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(p.B + (size_t)c * 2 * N * KP);
-                if (p.cluster > 1) {
+                if (pair) {
+                    // this CTA's row half of the chunk (hi and lo images are adjacent): one copy, no multicast
+                    bulk_g2s(dst, src + (size_t)crank * b_bytes, nbytes, b_full(s));
+                } else if (p.cluster > 1) {
                     // each CTA fetches 1/cluster of the chunk from L2 and multicasts it to all
                     const uint32_t slice = nbytes / (uint32_t)p.cluster;
                     const uint32_t off = cluster_ctarank() * slice;
@@ -359,29 +420,47 @@ gmm_tc_kernel(const TcParams p) {
             }
             if (p.prof && blockIdx.x == 0) { p.prof[0] = w_prod; p.prof[1] = clock64() - t_begin; }
         }
+    } else if (warp == kMmaWarp && pair && !leader) {
+        // ======================= peer CTA of a pair: relays "my half of B has landed" to rank 0 ====
+        const int64_t total = my_tiles * NCH;
+        for (int64_t it = 0; it < total; ++it) {
+            const int s = (int)(it % S);
+            mbar_wait(b_full(s), (uint32_t)((it / S) & 1));
+            if (lane == 0) mbar_arrive_remote(mapa_rank(b_full(s), 0));
+            __syncwarp();
+        }
     } else if (warp == kMmaWarp) {
         // ======================= MMA issuer (whole warp runs the loop; one elected lane issues) ===
         {
             const uint32_t tmem_u = __shfl_sync(0xFFFFFFFFu, tmem_base, 0);
-            const uint32_t idesc = make_idesc_tf32(kTileM, N);
+            const uint32_t idesc = make_idesc_tf32(pair ? 2 * kTileM : kTileM, N);
             const int ksteps = (p.debug == 2 || p.debug == 3) ? 1 : KP / 8 - p.koff;   // three-pass k-steps
             const uint32_t a_base = smem_u32(a_smem), b_base = smem_u32(b_smem);
-            const uint64_t astep = (2u * (kTileM * 16u)) >> 4, bstep = (2u * ((uint32_t)N * 16u)) >> 4;
+            const uint64_t astep = (2u * (kTileM * 16u)) >> 4, bstep = (2u * ((uint32_t)NB * 16u)) >> 4;
             int64_t it = 0;
             long long w_a = 0, w_b = 0, w_acc = 0;
             const long long t_begin = clock64();
             for (int64_t tl = 0; tl < my_tiles; ++tl) {
                 const int ab = (int)(tl % AB);
                 const uint32_t aph = (uint32_t)((tl / AB) & 1);
-                TIMED_WAIT(a_full(ab), aph, w_a);
+                if (pair) { const long long _t0 = clock64(); mbar_wait_cluster(a_full(ab), aph); w_a += clock64() - _t0; }
+                else TIMED_WAIT(a_full(ab), aph, w_a);
                 const uint32_t a_hi = a_base + (uint32_t)ab * a_bytes;
                 for (int c = 0; c < NCH; ++c, ++it) {
                     const int s = (int)(it % S);
                     const uint32_t ph = (uint32_t)((it / S) & 1);
                     const int acc = (int)(it & 1);
                     const uint32_t accph = (uint32_t)((it >> 1) & 1);
-                    TIMED_WAIT(b_full(s), ph, w_b);
-                    TIMED_WAIT(acc_empty(acc), accph ^ 1, w_acc);
+                    if (pair) {
+                        long long _t0 = clock64();
+                        mbar_wait_cluster(b_full(s), ph);
+                        long long _t1 = clock64();
+                        mbar_wait_cluster(acc_empty(acc), accph ^ 1);
+                        w_b += _t1 - _t0; w_acc += clock64() - _t1;
+                    } else {
+                        TIMED_WAIT(b_full(s), ph, w_b);
+                        TIMED_WAIT(acc_empty(acc), accph ^ 1, w_acc);
+                    }
                     tc_fence_after();
                     // Descriptors differ from their k-step-0 value only in the start-address field
                     // (low word), which advances by two 16-byte K slices per k-step.
@@ -389,12 +468,12 @@ gmm_tc_kernel(const TcParams p) {
                     const uint32_t d_tmem = tmem_u + (uint32_t)(acc * N);
                     uint64_t dah = make_desc(a_hi, kTileM * 16u, 128u);
                     uint64_t dal = make_desc(a_hi + a_half, kTileM * 16u, 128u);
-                    uint64_t dbh = make_desc(b_hi, (uint32_t)N * 16u, 128u);
-                    uint64_t dbl = make_desc(b_hi + b_half, (uint32_t)N * 16u, 128u);
+                    uint64_t dbh = make_desc(b_hi, (uint32_t)NB * 16u, 128u);
+                    uint64_t dbl = make_desc(b_hi + b_half, (uint32_t)NB * 16u, 128u);
                     // one elected region per chunk: the descriptor bases move to uniform registers
                     // once and the k-step offsets are uniform adds (an elected region per k-step
                     // re-moved all twelve operands each time, ~40 issue cycles per MMA)
-                    if (elect_one()) {
+                    if (!pair && elect_one()) {
                         umma_tf32(d_tmem, dal, dbh, idesc, 0u);  // small terms first; first MMA overwrites
                         umma_tf32(d_tmem, dah, dbl, idesc, 1u);
                         umma_tf32(d_tmem, dah, dbh, idesc, 1u);
@@ -413,6 +492,25 @@ gmm_tc_kernel(const TcParams p) {
                         else umma_commit(b_empty(s));
                         umma_commit(acc_full(acc));  // accumulator ready for the epilogue
                         if (c == NCH - 1) umma_commit(a_empty(ab));
+                    }
+                    if (pair && elect_one()) {
+                        umma_tf32_2sm(d_tmem, dal, dbh, idesc, 0u);
+                        umma_tf32_2sm(d_tmem, dah, dbl, idesc, 1u);
+                        umma_tf32_2sm(d_tmem, dah, dbh, idesc, 1u);
+                        for (int kk = 1; kk < ksteps; ++kk) {
+                            dah += astep; dal += astep; dbh += bstep; dbl += bstep;
+                            umma_tf32_2sm(d_tmem, dal, dbh, idesc, 1u);
+                            umma_tf32_2sm(d_tmem, dah, dbl, idesc, 1u);
+                            umma_tf32_2sm(d_tmem, dah, dbh, idesc, 1u);
+                        }
+                        if (p.koff) {
+                            dah += astep; dbh += bstep;
+                            umma_tf32_2sm(d_tmem, dah, dbh, idesc, 1u);
+                        }
+                        // every release / ready signal goes to the same barrier of both CTAs of the pair
+                        umma_commit_2sm(b_empty(s), cmask);
+                        umma_commit_2sm(acc_full(acc), cmask);
+                        if (c == NCH - 1) umma_commit_2sm(a_empty(ab), cmask);
                     }
                     __syncwarp();
                 }
@@ -523,7 +621,8 @@ gmm_tc_kernel(const TcParams p) {
                 }
             }
             fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
-            mbar_arrive(a_full(ab));
+            if (pair && !leader) mbar_arrive_remote(mapa_rank(a_full(ab), 0));   // rank 0 issues for both tiles
+            else mbar_arrive(a_full(ab));
             if (CONVERT && p.xtma) {
                 // every loader thread has consumed the staged tile: refill the buffer for the next one
                 asm volatile("bar.sync 2, %0;" ::"n"(kLoaderThreads) : "memory");
@@ -557,7 +656,10 @@ gmm_tc_kernel(const TcParams p) {
             auto release_stage = [&](int acc) {
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(acc_empty(acc));
+                if (lane == 0) {
+                    if (pair && !leader) mbar_arrive_remote_relaxed(mapa_rank(acc_empty(acc), 0));
+                    else mbar_arrive(acc_empty(acc));
+                }
             };
             for (int c = 0; c < NCH; ++c, ++it) {
                 const int acc = (int)(it & 1);
@@ -696,7 +798,9 @@ gmm_tc_kernel(const TcParams p) {
             const uint32_t pph = (uint32_t)(tl & 1);
             // the merging/storing group alternates per tile so both groups carry the same load
             const int merger = (kEpiGroups == 2) ? (int)(tl & 1) : 0;
-            if (kEpiGroups == 2 && group != merger) {
+            if (kEpiGroups > 2 && group != 0) {
+                // (timing experiments with more epilogue groups only: their partial states are dropped)
+            } else if (kEpiGroups == 2 && group != merger) {
                 mbar_wait(part_empty, pph ^ 1);
                 part[0 * 128 + row] = mx;
                 if (CONVERT) {
@@ -764,7 +868,7 @@ gmm_tc_kernel(const TcParams p) {
     if (p.cluster > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into it
     if (warp == kMmaWarp) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (pair) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -781,6 +885,10 @@ int32_t launch_tc(const TcParams& p_in, size_t smem, cudaStream_t st) {
     p.cluster = (want_cluster >= 2 && p.ntiles >= 2 && (p.N * p.KP * 8) % 32 == 0) ? 2 : 1;
     unsigned grid = (unsigned)std::min<int64_t>(p.ntiles, sms);
     if (p.cluster == 2) grid &= ~1u;
+    // CTA-pair MMAs (cta_group::2): rank 0 of every cluster issues M = 256 instructions for both SMs
+    static const int want_pair = [] { const char* e = getenv("VCB_TC_PAIR"); return e ? atoi(e) : 0; }();
+    p.pair = (want_pair && p.cluster == 2 && p.N % 16 == 0 && p.Bpair) ? 1 : 0;
+    if (p.pair) p.B = p.Bpair;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
@@ -881,6 +989,7 @@ static void fill_common(const vcb_gmmmap& g, const double* dX, int64_t T, int64_
     const TcPlan plan = tc_plan(g.M, g.tc.KP, convert ? 2 * g.DP : g.DP, convert ? g.DP + 2 : 4);
     p.X = dX; p.T = T; p.ldx = ldx; p.xbar = g.d_xbar.p;
     p.B = convert ? g.tc.Bc.p : g.tc.Bw.p;
+    p.Bpair = convert ? g.tc.Bc2.p : g.tc.Bw2.p;
     p.cst = g.tc.cst.p;
     p.c1 = g.tc.c1; p.koff = g.tc.koff;
     p.D = g.D; p.KP = g.tc.KP; p.G = plan.G; p.N = plan.N;

@@ -313,7 +313,29 @@ int32_t build_gmmmap(const double* weights, const double* mu, const double* sigm
                 }
             }
         }
+        // row-half split of every chunk image for the CTA-pair kernels (each CTA of a pair holds N/2
+        // rows of B; LBO of the half image is (N/2)*16 bytes)
+        auto split_pair = [&](const std::vector<float>& img, int nch, int n) {
+            std::vector<float> out(img.size(), 0.0f);
+            if (n <= 0 || (n % 16)) return out;
+            const int h = n / 2, kc = tc.KP / 4;
+            for (int ch = 0; ch < nch; ++ch) {
+                const size_t cb = (size_t)ch * 2 * n * tc.KP;
+                for (int part = 0; part < 2; ++part)
+                    for (int j = 0; j < kc; ++j)
+                        for (int row = 0; row < n; ++row) {
+                            const int rk = row / h, r2 = row % h;
+                            const size_t src = cb + (size_t)part * n * tc.KP + (size_t)j * n * 4 + (size_t)(row >> 3) * 32 + (row & 7) * 4;
+                            const size_t dst = cb + (size_t)rk * n * tc.KP + (size_t)part * h * tc.KP + (size_t)j * h * 4 +
+                                               (size_t)(r2 >> 3) * 32 + (r2 & 7) * 4;
+                            for (int e = 0; e < 4; ++e) out[dst + e] = img[src + e];
+                        }
+            }
+            return out;
+        };
+        const std::vector<float> bc2 = split_pair(bc, tc.NCHC, tc.NC), bw2 = split_pair(bw, tc.NCHW, tc.NW);
         if (tc.Bc.upload(bc) != cudaSuccess || tc.Bw.upload(bw) != cudaSuccess ||
+            tc.Bc2.upload(bc2) != cudaSuccess || tc.Bw2.upload(bw2) != cudaSuccess ||
             tc.cst.upload(cpad) != cudaSuccess)
             return fail(VCB_ECUDA, "model upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
