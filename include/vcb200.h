@@ -172,6 +172,13 @@ int32_t vcb_align_batch(const double* src, const int64_t* src_off, const double*
                         const int64_t* tgt_off, int64_t npairs, int32_t D, double* newtgt,
                         int64_t* paths);
 
+/* vc(mapper, [fm[1,:]; push_delta(fm[2:end,:])]) fused (bin/vc.jl:76-82): fm holds the power row and
+ * the STATIC features only, (1+Ds, total); the delta rows are appended per utterance on the device
+ * (boundary quirk of src/datasets.jl:8-11 included) before the chunked conversion. out (1+Ds, total). */
+int32_t vcb_traj_vc_static_batch(const vcb_traj* t, const double* fm, int32_t rows, const int64_t* offsets,
+                                 int64_t nseq, int32_t chunk_limit, double* out);
+int32_t vcb_traj_vc_static_batch_dev(const vcb_traj* t, const double* dfm, int32_t rows, const int64_t* offsets,
+                                     int64_t nseq, int32_t chunk_limit, double* dout, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Global variance and differential models

@@ -27,3 +27,27 @@ def test_align(vcb, oracle):
     assert np.array_equal(nt, newtgt[:, :to[1]])
     with pytest.raises(vcb.DimensionMismatch):
         vcb.align(np.zeros((3, 4)), np.zeros((2, 4)))                 # src/align.jl:11-13
+
+
+def test_vc_static_batch_fuses_push_delta(vcb, oracle):
+    """bin/vc.jl:76-82: src = [src[1,:]; push_delta(src[2:end,:])]; vc(mapper, src) -- in one call."""
+    import torch
+    Ds = 24
+    gm = vcb.synth.random_joint_gmm(41, 8, 4 * Ds)
+    fm, off = vcb.synth.trajectory_utterances(gm, 4, (20, 70), 41)
+    static = np.asfortranarray(fm[:1 + Ds])                         # power row + static features
+    full = np.asfortranarray(np.concatenate(
+        [np.concatenate([static[:1, off[i]:off[i + 1]], oracle.push_delta(static[1:, off[i]:off[i + 1]])], axis=0)
+         for i in range(4)], axis=1))
+    ref = oracle.vc_traj_batch(oracle.GMMMap(*gm), 30, full, off)
+    t = vcb.TrajectoryGMMMap(vcb.GMMMap(*gm), 30)
+    out = vcb.vc_static_batch(t, static, off)
+    assert out.shape == ref.shape and np.array_equal(out[0], static[0])
+    assert np.abs(out - ref).max() <= 1e-4 * np.abs(ref).max()
+    two_step = np.concatenate(vcb.vc_batch(vcb.TrajectoryGMMMap(vcb.GMMMap(*gm), 30), full, off), axis=1)
+    assert np.array_equal(out, two_step)                            # same kernels, same inputs
+    d = torch.from_numpy(np.ascontiguousarray(static.T)).cuda()
+    outd = vcb.vc_static_batch(vcb.TrajectoryGMMMap(vcb.GMMMap(*gm), 30), d, off).cpu().numpy().T
+    assert np.array_equal(outd, out)
+    with pytest.raises(vcb.DimensionMismatch):
+        vcb.vc_static_batch(t, fm, off)                             # already has delta rows

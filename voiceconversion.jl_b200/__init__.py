@@ -31,7 +31,7 @@ from . import jld, shard, synth  # noqa: F401
 __all__ = [
     "AbstractConverter", "FrameByFrameConverter", "TrajectoryConverter", "GMMMapParam", "GMMMap",
     "TrajectoryGMMMap", "TrajectoryGVGMMMap", "VarianceScaling", "fvpostf", "fvpostf_", "diffgmm",
-    "fvconvert", "fvconvert_gv", "vc", "vc_batch", "ncomponents", "dim", "predict_proba",
+    "fvconvert", "fvconvert_gv", "vc", "vc_batch", "vc_static_batch", "ncomponents", "dim", "predict_proba",
     "predict", "constructW", "push_delta", "align", "align_batch", "DTWs", "DimensionMismatch",
     "PosDefException", "SingularException", "ArgumentError", "CudaError", "VCBError",
     "set_device", "device_count", "set_kernel_variant", "launch_count",
@@ -491,6 +491,30 @@ def vc_batch(c, fms, offsets=None, _split: bool = True, epochs: int = 100, alpha
     if offsets is not None and not _split:
         return (out,)
     return [np.asfortranarray(out[:, off[i]:off[i + 1]]) for i in range(len(off) - 1)]
+
+
+def vc_static_batch(c: TrajectoryGMMMap, fm, offsets):
+    """``vc(c, [fm[1,:]; push_delta(fm[2:end,:])])`` for a batch in one call (the pattern of
+    bin/vc.jl:76-82): ``fm`` is (1+Ds, total) -- power row and STATIC features -- column-major, or a
+    frame-major CUDA tensor (total, 1+Ds); the delta rows are appended on the device."""
+    L = _lib.lib()
+    limit = len(c)
+    Ds = c.dim // 2
+    off = np.ascontiguousarray(offsets, dtype=np.int64)
+    if _is_torch(fm):
+        import torch
+        _check_dev_tensor(fm)
+        total, rows = fm.shape
+        out = torch.empty((total, Ds + 1), dtype=torch.float64, device=fm.device)
+        _lib.check(L.vcb_traj_vc_static_batch_dev(c._h, _lib.ptr(fm), rows, _lib.ptr(off), len(off) - 1, limit,
+                                                  _lib.ptr(out), _stream_ptr()))
+    else:
+        fm = _f64(fm)
+        out = np.empty((Ds + 1, fm.shape[1]), order="F")
+        _lib.check(L.vcb_traj_vc_static_batch(c._h, _lib.ptr(fm), fm.shape[0], _lib.ptr(off), len(off) - 1, limit,
+                                              _lib.ptr(out)))
+    _update_len(c, off, limit)
+    return out
 
 
 def _update_len(c: TrajectoryGMMMap, off: np.ndarray, limit: int) -> None:

@@ -87,6 +87,8 @@ SIGNATURES = {
     "vcb_dtw_fit_batch": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "vcb_dtw_fit_batch_dev": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp]),
     "vcb_dtw_update": (_i32, [_vp, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "vcb_traj_vc_static_batch": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, _vp]),
+    "vcb_traj_vc_static_batch_dev": (_i32, [_vp, _vp, _i32, _vp, _i64, _i32, _vp, _vp]),
     "vcb_trajgv_create": (_i32, [_vp, _vp, _vp, C.POINTER(_vp)]),
     "vcb_trajgv_destroy": (_i32, [_vp]),
     "vcb_trajgv_convert_batch": (_i32, [_vp, _vp, _i32, _i64, _vp, _i64, _i32, _i32, C.c_double, _vp, _i64]),

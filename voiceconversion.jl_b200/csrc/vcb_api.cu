@@ -138,12 +138,20 @@ static int32_t traj_device(const vcb_traj& t, const double* dX, int64_t ldx, con
     VCB_CUDA(cudaMemcpyAsync(d_chunks, chunks.data(), chunks.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     const double* X0 = dX + base * ldx;
     VCB_TRY(argmax_device(g, X0, total, ldx, d_mhat, st));                       // src/trajectory_gmmmap.jl:82
+    // bucket the frames by arg-max mixture once; E_t / P_t E_t and the GV gradient run as per-mixture GEMMs
+    static const bool per_frame = [] { const char* e = getenv("VCB_TRAJ_E"); return e && e[0] == 'f'; }();
+    int* ws = nullptr;
+    int64_t npanels = 0;
+    if (!per_frame && total < (int64_t)1 << 31 && g.D <= 256) {
+        VCB_CUDA(sc.get(&ws, group_workspace_ints(g.M, total)));
+        VCB_TRY(group_frames_by_mixture(d_mhat, total, g.M, ws, &npanels, st));
+    }
     VCB_TRY(traj_solve_device(t, X0, ldx, d_mhat, d_chunks, nchunks, maxlen, total, dY + base * ldy, ldy,
-                              dEy ? dEy + base * g.D : nullptr, copy_power, st));
+                              dEy ? dEy + base * g.D : nullptr, copy_power, st, ws, npanels));
     if (dmhat) VCB_TRY(widen_mhat(d_mhat, total, dmhat + base, st));
     if (gvr.gv)      // src/trajectory_gmmmap.jl:150-171
         VCB_TRY(trajgv_ascent_device(*gvr.gv, dY + base * ldy, ldy, dEy + base * g.D, dmhat + base, d_chunks, nchunks,
-                                     total, gvr.epochs, gvr.alpha, st));
+                                     total, gvr.epochs, gvr.alpha, st, ws, npanels));
     return VCB_OK;
 }
 
@@ -522,6 +530,67 @@ int32_t vcb_traj_vc_batch(const vcb_traj* t, const double* fm, int32_t rows, con
     if (!fm || !out) return fail(VCB_EARG, "null argument");
     VCB_TRY(use_device_of(t->g->device));
     return traj_host(*t, fm + 1, rows, offsets, nseq, chunk_limit, out + 1, t->Ds + 1, nullptr, nullptr, true);
+    VCB_GUARD_END
+}
+
+// vc(mapper, [fm[1,:]; push_delta(fm[2:end,:])]) in one call (bin/vc.jl:76-82): the
+// delta features are appended on the device, per utterance, before the chunked trajectory conversion.
+static int32_t traj_static_device(const vcb_traj& t, const double* dfm, const int64_t* offsets, int64_t nseq,
+                                  int chunk_limit, double* dout, cudaStream_t st) {
+    const int Ds = t.Ds;
+    if (nseq <= 0) return VCB_OK;
+    const int64_t base = offsets[0], total = offsets[nseq] - base;
+    if (total <= 0) return VCB_OK;
+    Scratch sc(st);
+    double* dfull = nullptr;
+    int64_t* dOff = nullptr;
+    VCB_CUDA(sc.get(&dfull, (size_t)total * (2 * Ds + 1)));
+    VCB_CUDA(sc.get(&dOff, (size_t)nseq + 1));
+    std::vector<int64_t> rel(offsets, offsets + nseq + 1);
+    for (auto& o : rel) o -= base;
+    VCB_CUDA(cudaMemcpyAsync(dOff, rel.data(), rel.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    const double* src = dfm + base * (Ds + 1);
+    VCB_TRY(push_delta_strided_device(src + 1, Ds + 1, Ds, dOff, nseq, total, dfull + 1, 2 * Ds + 1, st));
+    VCB_CUDA(cudaMemcpy2DAsync(dfull, (size_t)(2 * Ds + 1) * sizeof(double), src, (size_t)(Ds + 1) * sizeof(double),
+                               sizeof(double), (size_t)total, cudaMemcpyDeviceToDevice, st));   // power row
+    return traj_device(t, dfull + 1, 2 * Ds + 1, rel.data(), nseq, chunk_limit, dout + base * (Ds + 1) + 1, Ds + 1, nullptr,
+                       nullptr, true, st);
+}
+
+int32_t vcb_traj_vc_static_batch_dev(const vcb_traj* t, const double* dfm, int32_t rows, const int64_t* offsets,
+                                     int64_t nseq, int32_t chunk_limit, double* dout, void* stream) {
+    VCB_GUARD_BEGIN
+    if (!t || !offsets || !dfm || !dout) return fail(VCB_EARG, "null argument");
+    if (nseq < 0) return fail(VCB_EARG, "negative nseq");
+    if (rows != t->Ds + 1) return fail(VCB_EDIM, "Inconsistent dimentions. (static frame has %d rows, 1 + dim(t)/2 = %d)", rows, t->Ds + 1);
+    VCB_TRY(use_device_of(t->g->device));
+    return traj_static_device(*t, dfm, offsets, nseq, chunk_limit, dout, (cudaStream_t)stream);
+    VCB_GUARD_END
+}
+
+int32_t vcb_traj_vc_static_batch(const vcb_traj* t, const double* fm, int32_t rows, const int64_t* offsets,
+                                 int64_t nseq, int32_t chunk_limit, double* out) {
+    VCB_GUARD_BEGIN
+    if (!t || !offsets || !fm || !out) return fail(VCB_EARG, "null argument");
+    if (nseq < 0) return fail(VCB_EARG, "negative nseq");
+    if (rows != t->Ds + 1) return fail(VCB_EDIM, "Inconsistent dimentions. (static frame has %d rows, 1 + dim(t)/2 = %d)", rows, t->Ds + 1);
+    if (nseq == 0) return VCB_OK;
+    VCB_TRY(use_device_of(t->g->device));
+    const int64_t base = offsets[0], total = offsets[nseq] - base;
+    if (total <= 0) return VCB_OK;
+    cudaStream_t st = nullptr;
+    Scratch sc(st);
+    double *dI = nullptr, *dO = nullptr;
+    const size_t n = (size_t)total * rows;
+    VCB_CUDA(sc.get(&dI, n));
+    VCB_CUDA(sc.get(&dO, n));
+    VCB_CUDA(cudaMemcpyAsync(dI, fm + base * rows, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    std::vector<int64_t> rel(offsets, offsets + nseq + 1);
+    for (auto& o : rel) o -= base;
+    VCB_TRY(traj_static_device(*t, dI, rel.data(), nseq, chunk_limit, dO, st));
+    VCB_CUDA(cudaMemcpyAsync(out + base * rows, dO, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    VCB_CUDA(cudaStreamSynchronize(st));
+    return VCB_OK;
     VCB_GUARD_END
 }
 

@@ -9,8 +9,8 @@ namespace {
 
 // out (2D, total): static copy on top, delta below; interior frames of each utterance get
 // -0.5 x[t-1] + 0.5 x[t+1], the first and last frame keep delta = static (the reference's quirk).
-__global__ void push_delta_kernel(const double* __restrict__ src, int D, const int64_t* __restrict__ off,
-                                  int64_t nseq, double* __restrict__ out) {
+__global__ void push_delta_kernel(const double* __restrict__ src, int64_t lds, int D, const int64_t* __restrict__ off,
+                                  int64_t nseq, double* __restrict__ out, int64_t ldo) {
     const int64_t s = blockIdx.x;
     if (s >= nseq) return;
     const int64_t b = off[s], T = off[s + 1] - b;
@@ -18,11 +18,11 @@ __global__ void push_delta_kernel(const double* __restrict__ src, int D, const i
          e += (int64_t)gridDim.y * blockDim.x) {
         const int64_t t = e / D;
         const int k = (int)(e - t * D);
-        const double x = src[(b + t) * D + k];
+        const double x = src[(b + t) * lds + k];
         double dl = x;
-        if (t >= 1 && t + 1 < T) dl = -0.5 * src[(b + t - 1) * D + k] + 0.5 * src[(b + t + 1) * D + k];
-        out[(b + t) * 2 * D + k] = x;
-        out[(b + t) * 2 * D + D + k] = dl;
+        if (t >= 1 && t + 1 < T) dl = -0.5 * src[(b + t - 1) * lds + k] + 0.5 * src[(b + t + 1) * lds + k];
+        out[(b + t) * ldo + k] = x;
+        out[(b + t) * ldo + D + k] = dl;
     }
 }
 
@@ -59,10 +59,15 @@ __global__ void align_post_kernel(const double* __restrict__ tgt, const int64_t*
 
 int32_t push_delta_device(const double* d_src, int D, const int64_t* d_off, int64_t nseq,
                           int64_t total, double* d_out, cudaStream_t st) {
+    return push_delta_strided_device(d_src, D, D, d_off, nseq, total, d_out, 2 * D, st);
+}
+
+int32_t push_delta_strided_device(const double* d_src, int64_t lds, int D, const int64_t* d_off, int64_t nseq,
+                                  int64_t total, double* d_out, int64_t ldo, cudaStream_t st) {
     if (total == 0 || nseq == 0) return VCB_OK;
     const int64_t avg = (total * D + nseq - 1) / nseq;
     dim3 grid((unsigned)nseq, (unsigned)std::max<int64_t>(1, std::min<int64_t>((avg + 255) / 256, 64)));
-    push_delta_kernel<<<grid, 256, 0, st>>>(d_src, D, d_off, nseq, d_out);
+    push_delta_kernel<<<grid, 256, 0, st>>>(d_src, lds, D, d_off, nseq, d_out, ldo);
     count_launch();
     VCB_CUDA(cudaGetLastError());
     return VCB_OK;

@@ -316,7 +316,9 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
         acc_var += clock64() - _t0;                                 \
     } while (0)
 
-template <int DP, bool CONVERT>
+// PAIR: CTA-pair MMAs (cta_group::2).  A separate instantiation because a kernel that contains
+// cta_group::2 instructions can only be launched in clusters of two.
+template <int DP, bool CONVERT, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 gmm_tc_kernel(const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -324,7 +326,7 @@ gmm_tc_kernel(const TcParams p) {
     // and the issuing warp's descriptors can live in uniform registers (CUTLASS canonical_warp_idx_sync)
     const int warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int KP = p.KP, N = p.N, NCH = p.NCH, AB = p.abufs;
-    const bool pair = p.pair != 0;
+    constexpr bool pair = PAIR;
     const uint32_t crank = (p.cluster > 1) ? cluster_ctarank() : 0u;
     const bool leader = crank == 0;
     const int NB = pair ? N / 2 : N;                 // rows of B held by this CTA
@@ -379,7 +381,10 @@ gmm_tc_kernel(const TcParams p) {
         mbar_init(x_full, 1);
         fence_barrier_init();
     }
-    if (warp == kMmaWarp) { if (pair) tmem_alloc2(smem_u32(tmem_slot), 512); else tmem_alloc(smem_u32(tmem_slot), 512); }
+    if (warp == kMmaWarp) {
+        if constexpr (PAIR) tmem_alloc2(smem_u32(tmem_slot), 512);
+        else tmem_alloc(smem_u32(tmem_slot), 512);
+    }
     tc_fence_before();
     __syncthreads();
     if (p.cluster > 1) cluster_sync_all();   // peers' barriers are initialised before any remote arrive / multicast
@@ -493,7 +498,7 @@ gmm_tc_kernel(const TcParams p) {
                         umma_commit(acc_full(acc));  // accumulator ready for the epilogue
                         if (c == NCH - 1) umma_commit(a_empty(ab));
                     }
-                    if (pair && elect_one()) {
+                    if constexpr (PAIR) if (elect_one()) {
                         umma_tf32_2sm(d_tmem, dal, dbh, idesc, 0u);
                         umma_tf32_2sm(d_tmem, dah, dbl, idesc, 1u);
                         umma_tf32_2sm(d_tmem, dah, dbh, idesc, 1u);
@@ -868,7 +873,8 @@ gmm_tc_kernel(const TcParams p) {
     if (p.cluster > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into it
     if (warp == kMmaWarp) {
         tc_fence_after();
-        if (pair) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+        if constexpr (PAIR) tmem_dealloc2(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -878,8 +884,6 @@ int32_t launch_tc(const TcParams& p_in, size_t smem, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     TcParams p = p_in;
-    auto k = gmm_tc_kernel<DP, CONVERT>;
-    VCB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     static const int want_cluster = [] { const char* e = getenv("VCB_TC_CLUSTER"); return e ? atoi(e) : 2; }();
     // clusters of two share the B stream when there are at least two tiles per cluster to amortise it
     p.cluster = (want_cluster >= 2 && p.ntiles >= 2 && (p.N * p.KP * 8) % 32 == 0) ? 2 : 1;
@@ -888,7 +892,13 @@ int32_t launch_tc(const TcParams& p_in, size_t smem, cudaStream_t st) {
     // CTA-pair MMAs (cta_group::2): rank 0 of every cluster issues M = 256 instructions for both SMs
     static const int want_pair = [] { const char* e = getenv("VCB_TC_PAIR"); return e ? atoi(e) : 0; }();
     p.pair = (want_pair && p.cluster == 2 && p.N % 16 == 0 && p.Bpair) ? 1 : 0;
+    // pair kernels are instantiated for the C1 / C2 shapes only (experimental)
+    constexpr bool kHasPair = (CONVERT && DP == 24) || (!CONVERT && DP == 48);
+    if (!kHasPair) p.pair = 0;
     if (p.pair) p.B = p.Bpair;
+    auto k = gmm_tc_kernel<DP, CONVERT, false>;
+    if constexpr (kHasPair) { if (p.pair) k = gmm_tc_kernel<DP, CONVERT, true>; }
+    VCB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);

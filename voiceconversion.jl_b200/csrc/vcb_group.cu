@@ -1,0 +1,241 @@
+// vcb_group.cu -- per-mixture grouped Float64 products for the trajectory path.
+//
+// E_t = muy_m + A_m (x_t - mux_m) and g_t = P_m E_t (reference src/trajectory_gmmmap.jl:85-89 and the
+// right-hand side of :103-105) use the matrices of the arg-max mixture m = mhat_t of every frame.  A
+// per-frame mat-vec streams 2 x 18 KB of A_m / P_m from L2 for 48 outputs; instead the frames are
+// bucketed by mixture (counting sort, order inside a bucket irrelevant) and every CTA multiplies one
+// mixture's matrices, held in shared memory, with a 64-frame panel: a Float64 GEMM per mixture.
+// The same kernel serves the GV gradient (h_t = P_m (E_t - (W y)_t), src/trajectory_gmmmap.jl:161).
+#include "vcb_kernels.h"
+
+namespace vcb {
+
+namespace {
+
+constexpr int kFT = 64;          // frames per CTA panel
+constexpr int kFP = kFT + 2;     // padded panel row (keeps 16-byte alignment, spreads banks)
+
+__global__ void group_hist_kernel(const int32_t* __restrict__ mhat, int64_t total, int* __restrict__ hist) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < total) atomicAdd(&hist[mhat[t]], 1);
+}
+
+// one block: bucket starts, panel starts, scatter cursors
+__global__ void group_scan_kernel(const int* __restrict__ hist, int M, int* __restrict__ mstart,
+                                  int* __restrict__ tstart, int* __restrict__ cursor) {
+    if (threadIdx.x == 0) {
+        int a = 0, b = 0;
+        for (int m = 0; m < M; ++m) {
+            mstart[m] = a; tstart[m] = b; cursor[m] = a;
+            a += hist[m];
+            b += (hist[m] + kFT - 1) / kFT;
+        }
+        mstart[M] = a; tstart[M] = b;
+    }
+}
+
+__global__ void group_scatter_kernel(const int32_t* __restrict__ mhat, int64_t total, int* __restrict__ cursor,
+                                     int32_t* __restrict__ perm) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < total) perm[atomicAdd(&cursor[mhat[t]], 1)] = (int32_t)t;
+}
+
+struct GroupParams {
+    const int32_t* perm; const int* mstart; const int* tstart; int M;
+    const double* A; const double* mux; const double* muy; const double* P;   // per mixture, D2 x D2 column-major
+    int D2;
+    // MODE 0: panel = x - mux;  E = muy + A panel (-> E, Eout);  G = P E (-> G)
+    const double* X; int64_t ldx; double* E; double* Eout; double* G;
+    // MODE 1: panel = E - (W y);  H = P panel (-> G)
+    const double* Y; int64_t ldy; const unsigned char* edge;
+};
+
+// out[4][4] += Mat[i0..i0+3][k] * panel[k][f0..f0+3] over k
+__device__ __forceinline__ void panel_product(const double* __restrict__ mat, int ldm, const double* __restrict__ pan,
+                                              int D2, int i0, int f0, double (&o)[4][4]) {
+#pragma unroll 2
+    for (int k = 0; k < D2; ++k) {
+        const double2 a01 = *reinterpret_cast<const double2*>(mat + (size_t)k * ldm + i0);
+        const double2 a23 = *reinterpret_cast<const double2*>(mat + (size_t)k * ldm + i0 + 2);
+        const double2 b01 = *reinterpret_cast<const double2*>(pan + (size_t)k * kFP + f0);
+        const double2 b23 = *reinterpret_cast<const double2*>(pan + (size_t)k * kFP + f0 + 2);
+        const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) o[r][c] = fma(a[r], b[c], o[r][c]);
+    }
+}
+
+template <int MODE>
+__global__ void group_panel_kernel(const GroupParams p) {
+    extern __shared__ __align__(16) double sm[];
+    const int D2 = p.D2, D2p = (D2 + 3) & ~3;
+    double* mat = sm;                          // [D2][D2p]  (column k at mat + k*D2p)
+    double* pan = mat + (size_t)D2 * D2p;      // [D2][kFP]  panel, row k = reduction index
+    double* mid = pan + (size_t)D2 * kFP;      // [D2][kFP]  E panel (MODE 0)
+    __shared__ int s_m, s_first, s_n;
+    if (threadIdx.x == 0) {
+        const int tile = blockIdx.x;
+        int lo = 0, hi = p.M;                  // largest m with tstart[m] <= tile
+        while (hi - lo > 1) { const int mid_m = (lo + hi) >> 1; if (p.tstart[mid_m] <= tile) lo = mid_m; else hi = mid_m; }
+        const bool live = tile < p.tstart[p.M];
+        const int first = p.mstart[lo] + (tile - p.tstart[lo]) * kFT;
+        s_m = lo; s_first = first; s_n = live ? min(kFT, p.mstart[lo + 1] - first) : 0;
+    }
+    __syncthreads();
+    const int m = s_m, nf = s_n;
+    if (nf <= 0) return;
+    const int32_t* frames = p.perm + s_first;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int TI = D2p >> 2, ti = tid % TI, tf = tid / TI;     // thread tile: rows 4 ti.., frames 4 tf..
+    const int i0 = 4 * ti, f0 = 4 * tf;
+    const bool worker = tf < kFT / 4;
+    auto load_mat = [&](const double* src) {
+        for (int e = tid; e < D2 * D2p; e += nth) {
+            const int k = e / D2p, i = e - k * D2p;
+            mat[e] = (i < D2) ? src[(size_t)m * D2 * D2 + i + (size_t)k * D2] : 0.0;
+        }
+    };
+    // ---- panel
+    for (int e = tid; e < kFT * D2; e += nth) {
+        const int f = e / D2, k = e - f * D2;
+        double v = 0.0;
+        if (f < nf) {
+            const int64_t t = frames[f];
+            if (MODE == 0) {
+                v = p.X[t * p.ldx + k] - p.mux[(size_t)m * D2 + k];
+            } else {
+                const int Ds = D2 >> 1;
+                double wy;
+                if (k < Ds) {
+                    wy = p.Y[t * p.ldy + k];
+                } else {
+                    const unsigned char ed = p.edge[t];
+                    wy = 0.0;
+                    if (!(ed & 1)) wy = -0.5 * p.Y[(t - 1) * p.ldy + k - Ds];
+                    if (!(ed & 2)) wy = fma(0.5, p.Y[(t + 1) * p.ldy + k - Ds], wy);
+                }
+                v = p.E[t * D2 + k] - wy;
+            }
+        }
+        pan[(size_t)k * kFP + f] = v;
+    }
+    load_mat(MODE == 0 ? p.A : p.P);
+    __syncthreads();
+    double o[4][4];
+    if (MODE == 0) {
+        // ---- E = muy + A panel
+        if (worker) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const double b = (i0 + r < D2) ? p.muy[(size_t)m * D2 + i0 + r] : 0.0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) o[r][c] = b;
+            }
+            panel_product(mat, D2p, pan, D2, i0, f0, o);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int f = f0 + c;
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    if (i0 + r < D2) mid[(size_t)(i0 + r) * kFP + f] = o[r][c];
+                if (f < nf) {
+                    const int64_t t = frames[f];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        if (i0 + r < D2) {
+                            p.E[t * D2 + i0 + r] = o[r][c];
+                            if (p.Eout) p.Eout[t * D2 + i0 + r] = o[r][c];
+                        }
+                }
+            }
+        }
+        __syncthreads();
+        load_mat(p.P);
+        __syncthreads();
+    }
+    // ---- G = P (E panel | GV panel)
+    if (worker) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) o[r][c] = 0.0;
+        panel_product(mat, D2p, MODE == 0 ? mid : pan, D2, i0, f0, o);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int f = f0 + c;
+            if (f < nf) {
+                const int64_t t = frames[f];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    if (i0 + r < D2) p.G[t * D2 + i0 + r] = o[r][c];
+            }
+        }
+    }
+}
+
+}  // namespace
+
+size_t group_workspace_ints(int M, int64_t total) { return (size_t)total + 4 * (size_t)(M + 1); }
+
+// Buckets the frames by mixture.  ws: group_workspace_ints() ints.  Returns the number of panels in
+// *npanels_bound (an upper bound that needs no device read-back: total/kFT + M).
+int32_t group_frames_by_mixture(const int32_t* d_mhat, int64_t total, int M, int* ws, int64_t* npanels_bound,
+                                cudaStream_t st) {
+    int* hist = ws;
+    int* mstart = ws + (M + 1);
+    int* tstart = ws + 2 * (M + 1);
+    int* cursor = ws + 3 * (M + 1);
+    int32_t* perm = ws + 4 * (M + 1);
+    VCB_CUDA(cudaMemsetAsync(hist, 0, (size_t)(M + 1) * sizeof(int), st));
+    const unsigned g = (unsigned)((total + 255) / 256);
+    group_hist_kernel<<<g, 256, 0, st>>>(d_mhat, total, hist);
+    group_scan_kernel<<<1, 32, 0, st>>>(hist, M, mstart, tstart, cursor);
+    group_scatter_kernel<<<g, 256, 0, st>>>(d_mhat, total, cursor, perm);
+    count_launch(); count_launch(); count_launch();
+    VCB_CUDA(cudaGetLastError());
+    *npanels_bound = total / kFT + M;
+    return VCB_OK;
+}
+
+static int32_t launch_group(int mode, GroupParams& p, const int* ws, int M, int64_t npanels, cudaStream_t st) {
+    p.mstart = ws + (M + 1);
+    p.tstart = ws + 2 * (M + 1);
+    p.perm = ws + 4 * (M + 1);
+    p.M = M;
+    const int D2p = (p.D2 + 3) & ~3, TI = D2p / 4;
+    const int threads = std::min(1024, round_up(TI * (kFT / 4), 32));
+    if (TI * (kFT / 4) > 1024) return fail(VCB_EUNSUPPORTED, "feature dimension %d too large for the grouped product", p.D2);
+    const size_t smem = ((size_t)p.D2 * D2p + 2 * (size_t)p.D2 * kFP) * sizeof(double);
+    if (mode == 0) {
+        VCB_CUDA(cudaFuncSetAttribute(group_panel_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        group_panel_kernel<0><<<(unsigned)npanels, threads, smem, st>>>(p);
+    } else {
+        VCB_CUDA(cudaFuncSetAttribute(group_panel_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        group_panel_kernel<1><<<(unsigned)npanels, threads, smem, st>>>(p);
+    }
+    count_launch();
+    VCB_CUDA(cudaGetLastError());
+    return VCB_OK;
+}
+
+int32_t group_e_step(const vcb_traj& tr, const int* ws, int64_t npanels, const double* dX, int64_t ldx, double* dE,
+                     double* dEout, double* dG, cudaStream_t st) {
+    const vcb_gmmmap& g = *tr.g;
+    GroupParams p{};
+    p.A = g.d_A.p; p.mux = g.d_mux.p; p.muy = g.d_muy.p; p.P = tr.d_P.p; p.D2 = g.D;
+    p.X = dX; p.ldx = ldx; p.E = dE; p.Eout = dEout; p.G = dG;
+    return launch_group(0, p, ws, g.M, npanels, st);
+}
+
+int32_t group_gv_step(const vcb_traj& tr, const int* ws, int64_t npanels, const double* dY, int64_t ldy,
+                      const double* dE, const unsigned char* d_edge, double* dH, cudaStream_t st) {
+    const vcb_gmmmap& g = *tr.g;
+    GroupParams p{};
+    p.P = tr.d_P.p; p.D2 = g.D; p.E = const_cast<double*>(dE); p.G = dH;
+    p.Y = dY; p.ldy = ldy; p.edge = d_edge;
+    return launch_group(1, p, ws, g.M, npanels, st);
+}
+
+}  // namespace vcb

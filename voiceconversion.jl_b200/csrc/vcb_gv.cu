@@ -160,7 +160,7 @@ int32_t variance_scaling_device(const double* d_s2, int D, const double* dX, int
 
 int32_t trajgv_ascent_device(const vcb_trajgv& v, double* dY, int64_t ldy, const double* dE, const int64_t* d_mhat,
                              const int64_t* d_chunk_off, int64_t nchunks, int64_t total, int epochs, double alpha,
-                             cudaStream_t st) {
+                             cudaStream_t st, const int* ws, int64_t npanels) {
     const vcb_traj& tr = *v.t;
     const int Ds = tr.Ds, D2 = 2 * Ds;
     if (total == 0 || nchunks == 0) return VCB_OK;
@@ -180,9 +180,14 @@ int32_t trajgv_ascent_device(const vcb_trajgv& v, double* dY, int64_t ldy, const
     const int uth = std::min(1024, round_up(std::max(Ds * 8, 256), 32));
     const size_t usm = (size_t)(3 * Ds + (uth / Ds) * Ds) * sizeof(double);
     for (int e = 0; e < epochs && rc == VCB_OK; ++e) {
-        gv_h_kernel<<<hgrid, hblock, (size_t)fpb * D2 * sizeof(double), st>>>(dY, ldy, dE, d_mhat, d_edge, tr.d_P.p, Ds, total, dH);
+        if (ws) {
+            rc = group_gv_step(tr, ws, npanels, dY, ldy, dE, d_edge, dH, st);
+            if (rc != VCB_OK) break;
+        } else {
+            gv_h_kernel<<<hgrid, hblock, (size_t)fpb * D2 * sizeof(double), st>>>(dY, ldy, dE, d_mhat, d_edge, tr.d_P.p, Ds, total, dH);
+            count_launch();
+        }
         gv_update_kernel<<<(unsigned)nchunks, uth, usm, st>>>(dY, ldy, dH, d_chunk_off, v.d_muv.p, v.d_pv.p, Ds, alpha, derr);
-        count_launch();
         count_launch();
     }
     if (rc == VCB_OK && cudaGetLastError() != cudaSuccess) rc = fail(VCB_ECUDA, "GV ascent launch failed");

@@ -45,7 +45,18 @@ int32_t tc_argmax(const vcb_gmmmap& g, const double* dX, int64_t T, int64_t ldx,
 int32_t traj_solve_device(const vcb_traj& t, const double* dX, int64_t ldx, const int32_t* d_mhat,
                           const int64_t* d_chunk_off, int64_t nchunks, int max_chunk_len,
                           int64_t total_frames, double* dY, int64_t ldy, double* dEy_out,
-                          bool copy_power, cudaStream_t st);
+                          bool copy_power, cudaStream_t st, const int* ws = nullptr, int64_t npanels = 0);
+
+// ---- per-mixture grouped Float64 products (vcb_group.cu)
+size_t group_workspace_ints(int M, int64_t total);
+int32_t group_frames_by_mixture(const int32_t* d_mhat, int64_t total, int M, int* ws, int64_t* npanels_bound,
+                                cudaStream_t st);
+// E_t = muy_m + A_m (x_t - mux_m), g_t = P_m E_t for all frames (d_mhat 0-based buckets in ws)
+int32_t group_e_step(const vcb_traj& tr, const int* ws, int64_t npanels, const double* dX, int64_t ldx, double* dE,
+                     double* dEout, double* dG, cudaStream_t st);
+// h_t = P_m (E_t - (W y)_t)
+int32_t group_gv_step(const vcb_traj& tr, const int* ws, int64_t npanels, const double* dY, int64_t ldy,
+                      const double* dE, const unsigned char* d_edge, double* dH, cudaStream_t st);
 
 // ---- GV helpers (vcb_gv.cu)
 int32_t variance_scaling_device(const double* d_s2, int D, const double* dX, int64_t ldx, const int64_t* d_off,
@@ -53,11 +64,14 @@ int32_t variance_scaling_device(const double* d_s2, int D, const double* dX, int
 // gradient ascent of fvconvert(tgv, X) on the solved trajectories dY (in place); d_mhat 1-based
 int32_t trajgv_ascent_device(const vcb_trajgv& v, double* dY, int64_t ldy, const double* dE, const int64_t* d_mhat,
                              const int64_t* d_chunk_off, int64_t nchunks, int64_t total, int epochs, double alpha,
-                             cudaStream_t st);
+                             cudaStream_t st, const int* ws = nullptr, int64_t npanels = 0);
 
 // ---- callers either side (vcb_aux.cu)
 int32_t push_delta_device(const double* d_src, int D, const int64_t* d_off, int64_t nseq,
                           int64_t total, double* d_out, cudaStream_t st);
+// same with leading dimensions: src rows of length lds (D used), out rows of length ldo (2D written)
+int32_t push_delta_strided_device(const double* d_src, int64_t lds, int D, const int64_t* d_off, int64_t nseq,
+                                  int64_t total, double* d_out, int64_t ldo, cudaStream_t st);
 int32_t align_post_device(const double* d_tgt, const int64_t* d_soff_src, const int64_t* d_soff_tgt,
                           const int64_t* d_paths, int64_t npairs, int D, double* d_newtgt,
                           cudaStream_t st);

@@ -489,7 +489,7 @@ static int32_t launch_tiled(const TrajParams& p, int64_t nchunks, cudaStream_t s
 int32_t traj_solve_device(const vcb_traj& tr, const double* dX, int64_t ldx, const int32_t* d_mhat,
                           const int64_t* d_chunk_off, int64_t nchunks, int max_chunk_len,
                           int64_t total, double* dY, int64_t ldy, double* dEy_out, bool copy_power,
-                          cudaStream_t st) {
+                          cudaStream_t st, const int* ws, int64_t npanels) {
     (void)max_chunk_len;
     if (total == 0 || nchunks == 0) return VCB_OK;
     const vcb_gmmmap& g = *tr.g;
@@ -508,7 +508,10 @@ int32_t traj_solve_device(const vcb_traj& tr, const double* dX, int64_t ldx, con
     VCB_CUDA(cudaMallocAsync((void**)&dZ, (size_t)total * Ds * sizeof(double), st));
     VCB_CUDA(cudaMallocAsync((void**)&derr, sizeof(int), st));
     VCB_CUDA(cudaMemsetAsync(derr, 0, sizeof(int), st));
-    {
+    if (ws) {
+        // frames bucketed by mixture: one Float64 GEMM per mixture panel (vcb_group.cu)
+        VCB_TRY(group_e_step(tr, ws, npanels, dX, ldx, dE, dEy_out, dG, st));
+    } else {
         const int tpf = round_up(D2, 32), fpb = std::max(1, 256 / tpf);
         const int groups = 1;   // more groups trade parallelism for L1 reuse of A_m / P_m; 1 measured fastest on B200
         const int64_t per_block = (int64_t)fpb * groups;
