@@ -890,8 +890,11 @@ int32_t launch_tc(const TcParams& p_in, size_t smem, cudaStream_t st) {
     unsigned grid = (unsigned)std::min<int64_t>(p.ntiles, sms);
     if (p.cluster == 2) grid &= ~1u;
     // CTA-pair MMAs (cta_group::2): rank 0 of every cluster issues M = 256 instructions for both SMs
-    static const int want_pair = [] { const char* e = getenv("VCB_TC_PAIR"); return e ? atoi(e) : 0; }();
-    p.pair = (want_pair && p.cluster == 2 && p.N % 16 == 0 && p.Bpair) ? 1 : 0;
+    // Default: on for the arg-max kernel (light epilogue, MMA-bound: 1.10 -> 0.94 ms at C2), off for the
+    // conversion kernel (epilogue-bound once the MMA stream is cheaper: no gain).  VCB_TC_PAIR=0/1 forces both.
+    static const int want_pair = [] { const char* e = getenv("VCB_TC_PAIR"); return e ? atoi(e) : -1; }();
+    const bool use_pair = want_pair < 0 ? !CONVERT : want_pair != 0;
+    p.pair = (use_pair && p.cluster == 2 && p.N % 16 == 0 && p.Bpair) ? 1 : 0;
     // pair kernels are instantiated for the C1 / C2 shapes only (experimental)
     constexpr bool kHasPair = (CONVERT && DP == 24) || (!CONVERT && DP == 48);
     if (!kHasPair) p.pair = 0;
