@@ -142,7 +142,7 @@ static int32_t traj_device(const vcb_traj& t, const double* dX, int64_t ldx, con
     static const bool per_frame = [] { const char* e = getenv("VCB_TRAJ_E"); return e && e[0] == 'f'; }();
     int* ws = nullptr;
     int64_t npanels = 0;
-    if (!per_frame && total < (int64_t)1 << 31 && g.D <= 256) {
+    if (!per_frame && total < (int64_t)1 << 31 && g.D <= 256 && g.M <= 4096) {
         VCB_CUDA(sc.get(&ws, group_workspace_ints(g.M, total)));
         VCB_TRY(group_frames_by_mixture(d_mhat, total, g.M, ws, &npanels, st));
     }
