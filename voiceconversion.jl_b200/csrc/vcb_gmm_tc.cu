@@ -10,25 +10,33 @@
 //
 // so that TMEM receives z_m = Linv_m (x - mux_m) and Ey_m = muy_m + A_m (x - mux_m) for G mixtures
 // per MMA chunk.  When D is a multiple of 8 the ones columns form their own k-step, which needs a
-// single MMA (hi*hi is exact for them) instead of three: 10 instead of 12 MMAs per chunk at D = 24.  fp32 accuracy is needed (real models have cond(Sxx) ~ 1e7; plain TF32 misses the
+// single MMA (hi*hi is exact for them) instead of three: 10 instead of 12 MMAs per chunk at D = 24.
+// fp32 accuracy is needed (real models have cond(Sxx) ~ 1e7; plain TF32 misses the
 // 1e-4 parity bar by three orders of magnitude), so both operands are split into tf32 hi + lo
 // and each k-step issues three MMAs (hi.hi, hi.lo, lo.hi) into the same fp32 accumulator.
 //
 // Warp roles (one persistent CTA per SM, 384 threads, clusters of two CTAs):
-//   warps 0-7  two epilogue groups (0-3 / 4-7), each taking every other mixture of a chunk: tcgen05.ld of
-//              their 32 TMEM lanes (one frame per thread), software-pipelined over the mixtures of
-//              a chunk, |z|^2 -> log-lik, online soft-max, posterior-weighted accumulation of Ey
-//              (conversion) or running top-2 (arg-max); the two partial states of a tile merge
-//              through shared memory.  Per-mixture means and log-likelihoods never leave the SM.
+//   warps 0-7  two epilogue groups (0-3 / 4-7), each taking every other mixture of a chunk: tcgen05.ld
+//              of their 32 TMEM lanes (one frame per thread) for both of the group's mixtures, then
+//              the accumulator stage is handed back (one mbarrier arrival per warp) BEFORE the
+//              arithmetic: |z|^2 -> log-lik, soft-max with a lazy running maximum, posterior-weighted
+//              accumulation of Ey (conversion) or running top-2 (arg-max).  The two partial states of
+//              a tile merge through shared memory; per-mixture means never leave the SM.
 //   warp 8     B producer: cp.async.bulk (TMA 1-D) of pre-packed operand images into a ring of
 //              stages; each CTA of the cluster fetches half of every chunk from L2 and multicasts
-//              it to both (all CTAs stream the same operand, L2->SM traffic was the co-limiter).
-//   warp 9     MMA issuer: one elected lane issues tcgen05.mma / tcgen05.commit (the stage-free
-//              commit is multicast to both CTAs); owns the TMEM allocation.
-//   warps 10-11 A loaders (two frame rows per thread): read Float64 frames, centre in Float64, split to tf32 hi/lo, write the
-//              UMMA K-major (no-swizzle) image to shared memory, double-buffered across tiles.
+//              it to both (pair mode: each CTA keeps only its own row half, no multicast).
+//   warp 9     MMA issuer: one elected lane issues a whole chunk's tcgen05.mma and the commits from
+//              one elected region; owns the TMEM allocation.  Pair mode (template PAIR, cta_group::2,
+//              M = 256): rank 0 of the cluster issues for both SMs, rank 1's warp 9 relays the
+//              arrival of its half of B to rank 0.
+//   warps 10-11 loaders / storers: the Float64 frames of a tile arrive by one bulk copy (conversion,
+//              contiguous input) or by direct loads, are centred in Float64, split into tf32 hi/lo
+//              with a bit mask and written as the UMMA K-major (no-swizzle) image, double-buffered
+//              across tiles; the same warps convert the merged fp32 result tile to Float64 and store
+//              it with coalesced rows, so the epilogue never waits on global stores.
 // Pipelines: smem B ring (full/empty), A double buffer (full/empty), TMEM accumulator double
-// buffer (full/empty) -- all mbarriers; tcgen05.commit signals the "empty"/"full" transitions.
+// buffer (full/empty), merge buffer (part_full / out_full / part_empty), staged input (x_full) --
+// all mbarriers; tcgen05.commit signals the "empty"/"full" transitions of the MMA side.
 #include <cstdlib>
 
 #include "vcb_kernels.h"
@@ -38,11 +46,11 @@ namespace vcb {
 namespace {
 
 constexpr int kTileM = 128;
-// Two epilogue groups split the mixtures of every chunk between them.  An accumulator stage
-// cycles through MMA -> commit -> epilogue -> release, and with N = 192 only two stages fit in
-// TMEM, so the chunk rate is (t_mma + t_epilogue + hand-off latency) / 2: halving the epilogue's
-// per-chunk latency (a ~450-cycle dependent chain per mixture) is what raises it.  The groups'
-// partial soft-max states merge through shared memory at the end of a tile.
+// Two epilogue groups split the mixtures of every chunk between them (with N = 192 only two
+// accumulator stages fit in TMEM, so a stage must come back quickly: each group reads its columns
+// and releases the stage before reducing them).  The groups' partial soft-max states merge through
+// shared memory at the end of a tile.  VCB_EPI_GROUPS / VCB_LOADER_WARPS other than 2 are for
+// timing experiments only (the 4-group merge is not implemented).
 #ifndef VCB_EPI_GROUPS
 #define VCB_EPI_GROUPS 2
 #endif
