@@ -290,60 +290,110 @@ int32_t vcb_gmmmap_vc_dev(const vcb_gmmmap* g, const double* dfm, int32_t rows, 
 
 // Host pipeline shared by convert / vc: frames are cut into slices that rotate through NSLOT
 // (stream, device-in, device-out) slots so H2D, kernel and D2H of neighbouring slices overlap.
+// The transfer is the whole cost (1 M frames: 200 MB each way against a 0.7 ms kernel), so the
+// schedule is built around PCIe: the first and last slices are small and double / halve (the
+// pipeline fills and drains in the time of a 16 Ki-frame copy instead of a 128 Ki-frame one), and
+// streams and staging buffers are kept between calls (one context per device and concurrent caller).
+namespace {
+constexpr int kSlots = 4;
+struct HostPipe {
+    int device = -1;
+    size_t in_elems = 0, out_elems = 0;
+    cudaStream_t st[kSlots] = {};
+    double* din[kSlots] = {};
+    double* dout[kSlots] = {};
+};
+std::mutex g_pipe_mu;
+std::vector<HostPipe*> g_pipe_pool;
+
+HostPipe* pipe_acquire(int device, size_t in_elems, size_t out_elems) {
+    HostPipe* p = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_pipe_mu);
+        for (size_t i = 0; i < g_pipe_pool.size(); ++i)
+            if (g_pipe_pool[i]->device == device) { p = g_pipe_pool[i]; g_pipe_pool.erase(g_pipe_pool.begin() + i); break; }
+    }
+    if (!p) {
+        p = new HostPipe();
+        p->device = device;
+        for (int s = 0; s < kSlots; ++s)
+            if (cudaStreamCreateWithFlags(&p->st[s], cudaStreamNonBlocking) != cudaSuccess) { delete p; return nullptr; }
+    }
+    if (p->in_elems < in_elems || p->out_elems < out_elems) {
+        for (int s = 0; s < kSlots; ++s) {
+            if (p->din[s]) cudaFree(p->din[s]);
+            if (p->dout[s]) cudaFree(p->dout[s]);
+            p->din[s] = p->dout[s] = nullptr;
+        }
+        p->in_elems = p->out_elems = 0;
+        for (int s = 0; s < kSlots; ++s)
+            if (cudaMalloc((void**)&p->din[s], in_elems * sizeof(double)) != cudaSuccess ||
+                cudaMalloc((void**)&p->dout[s], out_elems * sizeof(double)) != cudaSuccess) {
+                for (int q = 0; q < kSlots; ++q) { if (p->din[q]) cudaFree(p->din[q]); if (p->dout[q]) cudaFree(p->dout[q]); p->din[q] = p->dout[q] = nullptr; }
+                std::lock_guard<std::mutex> lk(g_pipe_mu);
+                g_pipe_pool.push_back(p);
+                return nullptr;
+            }
+        p->in_elems = in_elems;
+        p->out_elems = out_elems;
+    }
+    return p;
+}
+void pipe_release(HostPipe* p) {
+    std::lock_guard<std::mutex> lk(g_pipe_mu);
+    g_pipe_pool.push_back(p);
+}
+}  // namespace
+
 static int32_t fbf_host(const vcb_gmmmap& g, const double* X, int64_t T, int64_t ldx, double* Y,
                         int64_t ldy, bool whole_rows) {
     if (T == 0) return VCB_OK;
-    // 128 Ki-frame slices measured best on B200 (VCB_SLICE sweep: 64 Ki 5.5 ms, 128 Ki 5.3 ms,
-    // 256 Ki 5.7 ms for 1 M frames): smaller slices pay per-copy overhead, larger ones pipeline fill.
-    constexpr int NSLOT = 4;
+    // 128 Ki-frame slices measured best on B200 in steady state (VCB_SLICE sweep); VCB_SLICE_MIN is
+    // the size the ramps start from / end at.
     static const int64_t slice_frames = [] { const char* e = getenv("VCB_SLICE"); return e ? atoll(e) : 131072LL; }();
+    static const int64_t ramp_frames = [] { const char* e = getenv("VCB_SLICE_MIN"); return e ? atoll(e) : 16384LL; }();
     const int64_t slice = std::min<int64_t>(T, std::max<int64_t>(slice_frames, 128));
+    const int64_t ramp = std::min<int64_t>(slice, std::max<int64_t>(ramp_frames, 128));
     // whole_rows (vc): X/Y point at row 1 of (rows, T) matrices with ld == rows; the copies move
     // complete columns starting one double earlier (the power row).
     const int64_t pre = whole_rows ? 1 : 0;
-    cudaStream_t st[NSLOT];
-    double *din[NSLOT], *dout[NSLOT];
+    HostPipe* hp = pipe_acquire(g.device, (size_t)slice * ldx, (size_t)slice * ldy);
+    if (!hp) return fail(VCB_ECUDA, "staging allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
     int32_t rc = VCB_OK;
-    int made = 0;
-    for (int s = 0; s < NSLOT; ++s) { st[s] = nullptr; din[s] = dout[s] = nullptr; }
-    for (int s = 0; s < NSLOT && rc == VCB_OK; ++s) {
-        if (cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking) != cudaSuccess ||
-            cudaMallocAsync((void**)&din[s], (size_t)slice * ldx * sizeof(double), st[s]) != cudaSuccess ||
-            cudaMallocAsync((void**)&dout[s], (size_t)slice * ldy * sizeof(double), st[s]) != cudaSuccess)
-            rc = fail(VCB_ECUDA, "staging allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
-        ++made;
-    }
     int idx = 0;
-    for (int64_t b = 0; b < T && rc == VCB_OK; b += slice, idx = (idx + 1) % NSLOT) {
-        const int64_t n = std::min(slice, T - b);
+    int64_t next = ramp;        // size of the next slice while ramping up
+    for (int64_t b = 0; b < T && rc == VCB_OK; idx = (idx + 1) % kSlots) {
+        const int64_t left = T - b;
+        // ramp up by doubling; ramp down by halving what is left once less than two full slices remain
+        int64_t n = std::min(next, slice);
+        if (left <= 2 * n) n = (left > 2 * ramp || left > slice) ? (left + 1) / 2 : left;
+        n = std::min(n, std::min(left, slice));
+        next = std::min(slice, next * 2);
         const size_t in_elems = (size_t)(n - 1) * ldx + g.D + pre;
         const size_t out_elems = (size_t)(n - 1) * ldy + g.D + pre;
-        cudaStream_t s = st[idx];
-        if (cudaMemcpyAsync(din[idx], X + b * ldx - pre, in_elems * sizeof(double), cudaMemcpyHostToDevice, s) != cudaSuccess) {
+        cudaStream_t s = hp->st[idx];
+        double *din = hp->din[idx], *dout = hp->dout[idx];
+        if (cudaMemcpyAsync(din, X + b * ldx - pre, in_elems * sizeof(double), cudaMemcpyHostToDevice, s) != cudaSuccess) {
             rc = fail(VCB_ECUDA, "H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
             break;
         }
-        rc = convert_device(g, din[idx] + pre, n, ldx, dout[idx] + pre, ldy, whole_rows, s);
+        rc = convert_device(g, din + pre, n, ldx, dout + pre, ldy, whole_rows, s);
         if (rc != VCB_OK) break;
         if (whole_rows || ldy == g.D) {
-            if (cudaMemcpyAsync(Y + b * ldy - pre, dout[idx], out_elems * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess)
+            if (cudaMemcpyAsync(Y + b * ldy - pre, dout, out_elems * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess)
                 rc = fail(VCB_ECUDA, "D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
         } else {
             // strided output: only the D converted rows of each column belong to the caller
-            if (cudaMemcpy2DAsync(Y + b * ldy, ldy * sizeof(double), dout[idx], ldy * sizeof(double),
+            if (cudaMemcpy2DAsync(Y + b * ldy, ldy * sizeof(double), dout, ldy * sizeof(double),
                                   g.D * sizeof(double), n, cudaMemcpyDeviceToHost, s) != cudaSuccess)
                 rc = fail(VCB_ECUDA, "D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
         }
+        b += n;
     }
-    for (int s = 0; s < made; ++s) {
-        if (st[s]) {
-            if (cudaStreamSynchronize(st[s]) != cudaSuccess && rc == VCB_OK)
-                rc = fail(VCB_ECUDA, "conversion failed: %s", cudaGetErrorString(cudaGetLastError()));
-            if (din[s]) cudaFreeAsync(din[s], st[s]);
-            if (dout[s]) cudaFreeAsync(dout[s], st[s]);
-            cudaStreamDestroy(st[s]);
-        }
-    }
+    for (int s = 0; s < kSlots; ++s)
+        if (cudaStreamSynchronize(hp->st[s]) != cudaSuccess && rc == VCB_OK)
+            rc = fail(VCB_ECUDA, "conversion failed: %s", cudaGetErrorString(cudaGetLastError()));
+    pipe_release(hp);
     return rc;
 }
 
