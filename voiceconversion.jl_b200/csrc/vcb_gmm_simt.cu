@@ -67,8 +67,18 @@ recheck_argmax_kernel(const double* __restrict__ X, int64_t ldx, const int* __re
                 const int r = r0 + lane;
                 double z = 0.0;
                 if (r < D) {
-#pragma unroll 4
-                    for (int k = 0; k <= r0 + 31 && k < D; ++k) z = fma(lm[(size_t)k * D + r], xs[k] - mu[k], z);
+                    // four independent partial sums: the loop is a dependent-FMA latency chain otherwise
+                    const int kend = min(r0 + 32, D);
+                    double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
+                    int k = 0;
+                    for (; k + 3 < kend; k += 4) {
+                        z0 = fma(lm[(size_t)k * D + r], xs[k] - mu[k], z0);
+                        z1 = fma(lm[(size_t)(k + 1) * D + r], xs[k + 1] - mu[k + 1], z1);
+                        z2 = fma(lm[(size_t)(k + 2) * D + r], xs[k + 2] - mu[k + 2], z2);
+                        z3 = fma(lm[(size_t)(k + 3) * D + r], xs[k + 3] - mu[k + 3], z3);
+                    }
+                    for (; k < kend; ++k) z0 = fma(lm[(size_t)k * D + r], xs[k] - mu[k], z0);
+                    z = (z0 + z1) + (z2 + z3);
                 }
                 q = fma(z, z, q);
             }
