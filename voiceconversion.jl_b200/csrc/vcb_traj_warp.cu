@@ -17,8 +17,9 @@
 //     of the inverse it owns;
 //   * no __syncthreads anywhere: a CTA is one warp, so chunks never wait for each other.
 // Per frame the kernel issues ~240 DMMA (61 k FP64 FMA) -- the FP64 pipe is the roofline -- and
-// streams 24 tiles (12 KB at NT = 3) of factors to HBM for the back substitution, which re-reads
-// them once in fragment order (each lane reads exactly the bytes it wrote).
+// streams 15 tiles (7.5 KB at NT = 3: Linv_t and L[t][t-1]) of factors to HBM for the back
+// substitution, which re-reads them once in fragment order (each lane reads exactly the bytes it
+// wrote); L[t][t-2] = -1/4 Pdd Linv' is not stored, its product is rebuilt there.
 #include "vcb_kernels.h"
 #include "vcb_traj.h"
 
@@ -92,7 +93,7 @@ __device__ __forceinline__ double2 diag_inverse(const double2 d, double* sd, int
 
 template <int NT>
 struct WarpLayout {
-    static constexpr int DSP = 8 * NT, NL = NT * (NT + 1) / 2, NF = NT * NT, FT = NL + 2 * NF;
+    static constexpr int DSP = 8 * NT, NL = NT * (NT + 1) / 2, NF = NT * NT, FT = NL + NF;   // stored: Linv_t, L[t][t-1]
     __host__ __device__ static constexpr int low(int i, int j) { return i * (i + 1) / 2 + j; }
 };
 
@@ -341,8 +342,8 @@ __global__ void __launch_bounds__(32) traj_solve_warp(const TrajParams p) {
             }
 #pragma unroll
             for (int e = 0; e < NF; ++e) {
-                F[(NL + e) * 32] = G1[e];
-                F[(NL + NF + e) * 32] = G2[e];
+                F[(NL + e) * 32] = G1[e];     // L[t][t-2] is not stored: the back substitution rebuilds its
+                                              // product from P (L2-resident) and Linv_{t-2}
                 sLp[e][lane] = G1[e];       // all reads of the old L[t-1][t-2] are complete (warp-synchronous)
             }
         }
@@ -417,6 +418,9 @@ __global__ void __launch_bounds__(32) traj_solve_warp(const TrajParams p) {
     // =========================== backward: L' y = z ===========================================
     // y_t = Linv_t' (z_t - L[t+1][t]' y_{t+1} - L[t+2][t]' y_{t+2}); the transposed products reduce
     // over the row index r (lanes 4, 8, 16 apart) and leave their result in column layout.
+    // L[t+2][t] = R[t+2][t] Linv_t' with R[t+2][t] = -1/4 Pdd_{t+1} symmetric, so
+    // L[t+2][t]' y_{t+2} = Linv_t (R[t+2][t] y_{t+2}): two small mat-vecs with tiles that are already
+    // here (Linv_t) or L2-resident (P) instead of 9 more factor tiles per frame from HBM.
     double* const sy = &sz[0][0];   // ring of three, row-layout reads
 #pragma unroll
     for (int e = 0; e < 3 * DSP; e += 32)
@@ -429,7 +433,17 @@ __global__ void __launch_bounds__(32) traj_solve_warp(const TrajParams p) {
 #pragma unroll
         for (int e = 0; e < NF; ++e) {
             A1[e] = (t + 1 < T) ? F[(FT + NL + e) * 32] : zero2();
-            A2[e] = (t + 2 < T) ? F[(2 * FT + NL + NF + e) * 32] : zero2();
+            A2[e] = zero2();
+        }
+        if (t + 2 < T) {
+            const double* Pq = p.P + (size_t)mh[t + 1] * D2 * D2;
+#pragma unroll
+            for (int i = 0; i < NT; ++i)
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    const double2 v = ldq(Pq, Ds, Ds, i, j);
+                    A2[i * NT + j] = make_double2(-0.25 * v.x, -0.25 * v.y);
+                }
         }
 #pragma unroll
         for (int i = 0; i < NT; ++i) zr[i] = rok[i] ? Zg[(size_t)t * Ds + 8 * i + r] : 0.0;
@@ -438,18 +452,49 @@ __global__ void __launch_bounds__(32) traj_solve_warp(const TrajParams p) {
         const double* const y1 = sy + ((t + 1) % 3) * DSP;
         const double* const y2 = sy + ((t + 2) % 3) * DSP;
         double* const yt = sy + (t % 3) * DSP;
+        // u = R[t+2][t] y_{t+2} (row layout after the reduction over q), then v = Linv_t u
+        double v[NT];
+        {
+            double u[NT];
+#pragma unroll
+            for (int i = 0; i < NT; ++i) u[i] = 0.0;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const double2 yc = *reinterpret_cast<const double2*>(y2 + 8 * j + 2 * q);
+#pragma unroll
+                for (int i = 0; i < NT; ++i) u[i] = fma(A2[i * NT + j].x, yc.x, fma(A2[i * NT + j].y, yc.y, u[i]));
+            }
+#pragma unroll
+            for (int i = 0; i < NT; ++i) {
+                u[i] += __shfl_xor_sync(kFull, u[i], 1);
+                u[i] += __shfl_xor_sync(kFull, u[i], 2);
+                if (q == 0) sdiag[8 * i + r] = u[i];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < NT; ++i) v[i] = 0.0;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const double2 uc = *reinterpret_cast<const double2*>(sdiag + 8 * j + 2 * q);
+#pragma unroll
+                for (int i = j; i < NT; ++i) v[i] = fma(L[LY::low(i, j)].x, uc.x, fma(L[LY::low(i, j)].y, uc.y, v[i]));
+            }
+#pragma unroll
+            for (int i = 0; i < NT; ++i) {
+                v[i] += __shfl_xor_sync(kFull, v[i], 1);
+                v[i] += __shfl_xor_sync(kFull, v[i], 2);
+            }
+        }
         double2 acc[NT];
 #pragma unroll
         for (int j = 0; j < NT; ++j) acc[j] = zero2();
 #pragma unroll
         for (int i = 0; i < NT; ++i) {
-            const double a = y1[8 * i + r], b = y2[8 * i + r];
+            const double a = y1[8 * i + r];
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
                 acc[j].x = fma(A1[i * NT + j].x, a, acc[j].x);
                 acc[j].y = fma(A1[i * NT + j].y, a, acc[j].y);
-                acc[j].x = fma(A2[i * NT + j].x, b, acc[j].x);
-                acc[j].y = fma(A2[i * NT + j].y, b, acc[j].y);
             }
         }
 #pragma unroll
@@ -467,7 +512,7 @@ __global__ void __launch_bounds__(32) traj_solve_warp(const TrajParams p) {
         for (int j = 0; j < NT; ++j) out[j] = zero2();
 #pragma unroll
         for (int i = 0; i < NT; ++i) {
-            const double w = zr[i] - sw[8 * i + r];
+            const double w = zr[i] - sw[8 * i + r] - v[i];
 #pragma unroll
             for (int j = 0; j <= i; ++j) {
                 out[j].x = fma(L[LY::low(i, j)].x, w, out[j].x);
@@ -525,7 +570,7 @@ int32_t launch_warp(const TrajParams& p, int64_t nchunks, cudaStream_t st) {
 size_t traj_warp_factor_bytes(int Ds) {
     const int nt = (Ds + 7) / 8;
     if (nt < 1 || nt > 3) return 0;
-    return (size_t)(nt * (nt + 1) / 2 + 2 * nt * nt) * 32 * sizeof(double2);
+    return (size_t)(nt * (nt + 1) / 2 + nt * nt) * 32 * sizeof(double2);
 }
 
 int32_t traj_warp_launch(const TrajParams& p, int64_t nchunks, cudaStream_t st) {
