@@ -338,7 +338,7 @@ gmm_tc_kernel(const TcParams p) {
     const uint32_t crank = (p.cluster > 1) ? cluster_ctarank() : 0u;
     const bool leader = crank == 0;
     const int NB = pair ? N / 2 : N;                 // rows of B held by this CTA
-    const int S = pair ? min(kMaxStages, 2 * p.stages) : p.stages;   // half-size stages in pair mode
+    const int S = p.stages;                          // sized for this mode by tc_plan
     constexpr int ROWS = CONVERT ? 2 * DP : DP;  // TMEM columns per mixture
 
     // ---- shared memory carve-up
@@ -892,21 +892,9 @@ int32_t launch_tc(const TcParams& p_in, size_t smem, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     TcParams p = p_in;
-    static const int want_cluster = [] { const char* e = getenv("VCB_TC_CLUSTER"); return e ? atoi(e) : 2; }();
-    // clusters of two share the B stream when there are at least two tiles per cluster to amortise it
-    p.cluster = (want_cluster >= 2 && p.ntiles >= 2 && (p.N * p.KP * 8) % 32 == 0) ? 2 : 1;
     unsigned grid = (unsigned)std::min<int64_t>(p.ntiles, sms);
     if (p.cluster == 2) grid &= ~1u;
-    // CTA-pair MMAs (cta_group::2): rank 0 of every cluster issues M = 256 instructions for both SMs
-    // Default: on for the arg-max kernel (light epilogue, MMA-bound: 1.10 -> 0.94 ms at C2), off for the
-    // conversion kernel (epilogue-bound once the MMA stream is cheaper: no gain).  VCB_TC_PAIR=0/1 forces both.
-    static const int want_pair = [] { const char* e = getenv("VCB_TC_PAIR"); return e ? atoi(e) : -1; }();
-    const bool use_pair = want_pair < 0 ? !CONVERT : want_pair != 0;
-    p.pair = (use_pair && p.cluster == 2 && p.N % 16 == 0 && p.Bpair) ? 1 : 0;
-    // pair kernels are instantiated for the C1 / C2 shapes only (experimental)
-    constexpr bool kHasPair = (CONVERT && DP == 24) || (!CONVERT && DP == 48);
-    if (!kHasPair) p.pair = 0;
-    if (p.pair) p.B = p.Bpair;
+    constexpr bool kHasPair = (CONVERT && DP == 24) || (!CONVERT && DP == 48);   // keep in step with fill_common
     auto k = gmm_tc_kernel<DP, CONVERT, false>;
     if constexpr (kHasPair) { if (p.pair) k = gmm_tc_kernel<DP, CONVERT, true>; }
     VCB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -966,7 +954,9 @@ constexpr size_t kSmemLimit = 227 * 1024;
 
 }  // namespace
 
-TcPlan tc_plan(int M, int KP, int rows_per_mixture, int part_rows) {
+// pair: the plan is for CTA-pair MMAs, where a CTA stores only its row half of every B stage.
+// force_g: keep the packed number of mixtures per chunk and only size the buffers (launch time).
+TcPlan tc_plan(int M, int KP, int rows_per_mixture, int part_rows, bool pair, int force_g) {
     // Pick (mixtures per chunk, A buffers) by estimated tensor-pipe time per tile.  Measured on
     // B200 (tools/micro/umma_bench.cu): one thread issues a tcgen05.mma every ~84 cycles at best,
     // an M=128 x N x K=8 tf32 MMA executes in ~N/2 + 11 cycles.
@@ -980,11 +970,13 @@ TcPlan tc_plan(int M, int KP, int rows_per_mixture, int part_rows) {
     double best_cost = 1e30;
     for (int abufs = 2; abufs >= 1; --abufs) {
         for (int g = gmax; g >= 1; --g) {
+            if (force_g && g != force_g) continue;
             const int n = g * rows_per_mixture;
             if (n % 16) continue;
             const size_t a = (size_t)abufs * 2 * kTileM * KP * 4;
-            const size_t bst = (size_t)2 * n * KP * 4;
-            if (a + 2 * bst + extra > kSmemLimit) continue;
+            const size_t bst = ((size_t)2 * n * KP * 4) / (pair ? 2 : 1);
+            // a forced shape (the fallback of a pair-planned model to single-CTA MMAs) may run on one stage
+            if (a + (force_g ? 1 : 2) * bst + extra > kSmemLimit) continue;
             const int nch = (M + g - 1) / g;
             const double per_mma = std::max(84.0, n / 2.0 + 11.0);
             const double cost = (double)nch * ksteps * 3 * per_mma + (abufs == 1 ? 4000.0 : 0.0);
@@ -1007,10 +999,24 @@ bool tc_supported(const vcb_gmmmap& g, bool convert) {
 
 static void fill_common(const vcb_gmmmap& g, const double* dX, int64_t T, int64_t ldx, bool convert, TcParams& p,
                         size_t& smem) {
-    const TcPlan plan = tc_plan(g.M, g.tc.KP, convert ? 2 * g.DP : g.DP, convert ? g.DP + 2 : 4);
+    // cluster / pair decision (needs only the problem size), then the buffer plan for that mode
+    const int64_t ntiles = (T + kTileM - 1) / kTileM;
+    const int packedG = convert ? g.tc.GC : g.tc.GW, packedN = convert ? g.tc.NC : g.tc.NW;
+    static const int want_cluster = [] { const char* e = getenv("VCB_TC_CLUSTER"); return e ? atoi(e) : 2; }();
+    // clusters of two share the B stream when there are at least two tiles per cluster to amortise it
+    p.cluster = (want_cluster >= 2 && ntiles >= 2 && (packedN * g.tc.KP * 8) % 32 == 0) ? 2 : 1;
+    // CTA-pair MMAs (cta_group::2): rank 0 of every cluster issues M = 256 instructions for both SMs.
+    // Default: on for the arg-max kernel (light epilogue, MMA-bound), off for the conversion kernel
+    // (epilogue-bound once the MMA stream is cheaper: no gain).  VCB_TC_PAIR=0/1 forces both.
+    static const int want_pair = [] { const char* e = getenv("VCB_TC_PAIR"); return e ? atoi(e) : -1; }();
+    const bool use_pair = want_pair < 0 ? !convert : want_pair != 0;
+    const bool has_pair_kernel = (convert && g.DP == 24) || (!convert && g.DP == 48);   // instantiated shapes
+    p.pair = (use_pair && has_pair_kernel && p.cluster == 2 && packedN % 16 == 0) ? 1 : 0;
+    const TcPlan plan = tc_plan(g.M, g.tc.KP, convert ? 2 * g.DP : g.DP, convert ? g.DP + 2 : 4, p.pair != 0, packedG);
     p.X = dX; p.T = T; p.ldx = ldx; p.xbar = g.d_xbar.p;
     p.B = convert ? g.tc.Bc.p : g.tc.Bw.p;
     p.Bpair = convert ? g.tc.Bc2.p : g.tc.Bw2.p;
+    if (p.pair) p.B = p.Bpair;
     p.cst = g.tc.cst.p;
     p.c1 = g.tc.c1; p.koff = g.tc.koff;
     p.D = g.D; p.KP = g.tc.KP; p.G = plan.G; p.N = plan.N;

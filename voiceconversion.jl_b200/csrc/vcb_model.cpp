@@ -268,7 +268,9 @@ int32_t build_gmmmap(const double* weights, const double* mu, const double* sigm
             tc.KP = (kdata - D >= 2) ? kdata : kdata + 8;
             tc.koff = (kdata - D >= 2) ? 0 : 1;
         }
-        const TcPlan pc = tc_plan(M, tc.KP, 2 * DP, DP + 2), pw = tc_plan(M, tc.KP, DP, 4);
+        // the whitening-only (arg-max) kernel runs CTA-pair MMAs, where a CTA stores half of every B
+        // stage: plan its chunk width for that mode (the single-CTA fallback then runs on fewer stages)
+        const TcPlan pc = tc_plan(M, tc.KP, 2 * DP, DP + 2), pw = tc_plan(M, tc.KP, DP, 4, DP == 48);
         tc.GC = pc.G; tc.NC = pc.N; tc.NCHC = pc.G ? (M + pc.G - 1) / pc.G : 0;
         tc.GW = pw.G; tc.NW = pw.N; tc.NCHW = pw.G ? (M + pw.G - 1) / pw.G : 0;
         auto put = [&](std::vector<float>& img, size_t base, int rows, int n, int k, double v) {

@@ -23,6 +23,6 @@ struct TcPlan {
 };
 // rows_per_mixture = DP (whitening only) or 2*DP (whitening + regression); part_rows = floats per
 // frame of the epilogue groups' merge buffer.
-TcPlan tc_plan(int M, int KP, int rows_per_mixture, int part_rows);
+TcPlan tc_plan(int M, int KP, int rows_per_mixture, int part_rows, bool pair = false, int force_g = 0);
 
 }  // namespace vcb
