@@ -145,3 +145,33 @@ def test_full_c1_properties(vcb, oracle):
     assert np.abs(out[:, idx] - ref).max() <= tol_for(ref[1:])
     out_perm = vcb.vc(g, sub)
     assert np.array_equal(out_perm, out[:, idx])
+
+
+def test_host_calls_are_reentrant_across_threads(vcb, oracle):
+    """Handles are immutable and the host pipeline keeps one cached (streams, staging) context per
+    concurrent caller: four threads converting different matrices with one model get their own results."""
+    import threading
+    gm = vcb.synth.random_joint_gmm(23, 16, 48)
+    g = vcb.GMMMap(*gm)
+    fms = [vcb.synth.fbf_feature_matrix(gm, 20000 + 3000 * i, 50 + i) for i in range(4)]
+    outs, errs = [None] * 4, []
+
+    def work(i):
+        try:
+            for _ in range(3):
+                outs[i] = vcb.vc(g, fms[i])
+        except Exception as e:       # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs
+    og = oracle.GMMMap(*gm)
+    for i in range(4):
+        ref = og.vc(np.asfortranarray(fms[i][:, :1500]))
+        assert np.array_equal(outs[i][0], fms[i][0])
+        assert np.abs(outs[i][:, :1500] - ref).max() <= tol_for(ref)
+        assert np.array_equal(outs[i], vcb.vc(g, fms[i]))      # and the same as a serial call

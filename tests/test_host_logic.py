@@ -72,3 +72,27 @@ def test_fixture_model_properties(fixture_model):
     assert abs(w.sum() - 1) < 1e-12 and mu.shape == (80, 32) and sg.shape == (80, 80, 32)
     conds = [np.linalg.cond(sg[:40, :40, m]) for m in range(32)]
     assert max(conds) > 1e6           # the conditioning that rules out single-pass TF32
+
+
+def test_diffgmm_is_host_side_and_matches_the_oracle(vcb, oracle):
+    """vcb_diffgmm (src/diffgmm.jl:9-25) is a pure parameter transform: it runs without a GPU and is
+    bit-identical to the oracle's restatement; also no-GPU entry points of the GV family fail loudly."""
+    gm = vcb.synth.random_joint_gmm(17, 5, 12)
+    w, mo, so = vcb.diffgmm((gm.weights, gm.means, gm.covars))
+    om, os_ = oracle.diffgmm(gm.means, gm.covars)
+    assert np.array_equal(mo, om) and np.array_equal(so, os_) and w is gm.weights
+    d = vcb.diffgmm(gm)                                   # JointGMM named tuple in, same type out
+    assert type(d) is type(gm) and np.array_equal(d.means, om)
+    with pytest.raises(vcb.ArgumentError):
+        vcb.diffgmm((gm.weights, gm.means[:5], gm.covars[:5, :5]))     # odd joint dimension
+
+
+def test_gv_entry_points_need_a_gpu(vcb):
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("GPU present")
+    except ImportError:
+        pass
+    with pytest.raises(vcb.CudaError):
+        vcb.fvpostf(vcb.VarianceScaling(np.ones(3)), np.zeros((3, 8)))
