@@ -329,6 +329,23 @@ def main():
                                        "workload": "C2: 48-dim source (static+delta), 64 mixtures, 1000 utt x 500 frames, one chunk per utterance",
                                        "hbm_equiv_gbs": b_traj * fr / (ms * 1e-3) / 1e9}
             del dfm2
+            # C4's per-GPU shard: 128 mixtures, 1024 utterances x 500 frames (8192 utterances on 8 GPUs)
+            gm4, fm4, off4 = vcb.synth.config_c2(1024, 500, M=128, seed=1004)
+            tj4 = vcb.TrajectoryGMMMap(vcb.GMMMap(*gm4), 500)
+            dfm4 = torch.from_numpy(np.ascontiguousarray(fm4.T)).cuda()
+            for _ in range(2):
+                vcb.vc_batch(tj4, dfm4, off4, _split=False)
+            barrier()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(3):
+                vcb.vc_batch(tj4, dfm4, off4, _split=False)
+            e.record(); barrier()
+            ms = max_over_ranks(s.elapsed_time(e) / 3)
+            extras["trajectory_c4_shard"] = {"value": world * 1024 * 500 / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms,
+                                             "workload": "C4 shard: 128 mixtures, 1024 utt x 500 frames per GPU",
+                                             "hbm_equiv_gbs": b_traj * 1024 * 500 / (ms * 1e-3) / 1e9}
+            del dfm4, fm4
             tm, to, sq, so = vcb.synth.config_c3(1000)
             dtm = torch.from_numpy(np.ascontiguousarray(tm.T)).cuda(); dsq = torch.from_numpy(np.ascontiguousarray(sq.T)).cuda()
             d = vcb.DTWs.DTW(fstep=0, bstep=2)

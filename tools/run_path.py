@@ -18,7 +18,8 @@ def timeit(fn):
     return s.elapsed_time(e) / reps
 if which == "traj":
     n = int(os.environ.get("N_UTT", 1000)); limit = int(os.environ.get("LIMIT", 500))
-    gm, fm, off = vcb.synth.config_c2(n, 500)
+    M = int(os.environ.get("MIX", 64))
+    gm, fm, off = vcb.synth.config_c2(n, 500, M=M) if M != 64 else vcb.synth.config_c2(n, 500)
     t = vcb.TrajectoryGMMMap(vcb.GMMMap(*gm), limit)
     d = torch.from_numpy(np.ascontiguousarray(fm.T)).cuda()
     ms = timeit(lambda: vcb.vc_batch(t, d, off, _split=False))
