@@ -283,6 +283,24 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// packed fp32x2 arithmetic (FFMA2 / FMUL2): one issue slot for two lanes of the epilogue's FMAs
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 [[maybe_unused]] __device__ __forceinline__ float to_tf32(float v) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -699,15 +717,21 @@ gmm_tc_kernel(const TcParams p) {
                     // on the reference point).
                     constexpr float kLazy = 40.0f;
                     auto reduce2 = [&](const float (&va)[LOADW], const float (&vb)[LOADW], int g, bool two, float cma, float cmb) {
-                        float qa0 = 0.f, qa1 = 0.f, qb0 = 0.f, qb1 = 0.f;
+                        // |z|^2 with packed FMAs: two 2-wide partial sums per mixture
+                        uint64_t qa01 = 0ull, qa23 = 0ull, qb01 = 0ull, qb23 = 0ull;
 #pragma unroll
-                        for (int r = 0; r < DP; r += 2) {
-                            qa0 = fmaf(va[r], va[r], qa0);
-                            qa1 = fmaf(va[r + 1], va[r + 1], qa1);
-                            qb0 = fmaf(vb[r], vb[r], qb0);
-                            qb1 = fmaf(vb[r + 1], vb[r + 1], qb1);
+                        for (int r = 0; r < DP; r += 4) {
+                            const uint64_t a0 = pack2(va[r], va[r + 1]), a1 = pack2(va[r + 2], va[r + 3]);
+                            const uint64_t b0 = pack2(vb[r], vb[r + 1]), b1 = pack2(vb[r + 2], vb[r + 3]);
+                            qa01 = ffma2(a0, a0, qa01);
+                            qa23 = ffma2(a1, a1, qa23);
+                            qb01 = ffma2(b0, b0, qb01);
+                            qb23 = ffma2(b1, b1, qb23);
                         }
-                        const float qa = qa0 + qa1, qb = qb0 + qb1;
+                        float qa0, qa1, qa2, qa3, qb0, qb1, qb2, qb3;
+                        unpack2(qa01, qa0, qa1); unpack2(qa23, qa2, qa3);
+                        unpack2(qb01, qb0, qb1); unpack2(qb23, qb2, qb3);
+                        const float qa = (qa0 + qa1) + (qa2 + qa3), qb = (qb0 + qb1) + (qb2 + qb3);
                         const float la = fmaf(-0.5f, qa, cma);
                         const float lb = two ? fmaf(-0.5f, qb, cmb) : -INFINITY;
                         if (CONVERT) {
@@ -715,16 +739,26 @@ gmm_tc_kernel(const TcParams p) {
                             if (lm > mx + kLazy) {
                                 const float a = __expf(mx - lm);   // 0 on the first visit (mx = -inf)
                                 sum *= a;
+                                const uint64_t a2 = pack2(a, a);
 #pragma unroll
-                                for (int r = 0; r < DP; ++r) y[r] *= a;
+                                for (int r = 0; r < DP; r += 2) {
+                                    const uint64_t yy = fmul2(pack2(y[r], y[r + 1]), a2);
+                                    unpack2(yy, y[r], y[r + 1]);
+                                }
                                 mx = lm;
                             }
                             const float wa = (la == -INFINITY) ? 0.f : __expf(la - mx);
                             const float wb = (lb == -INFINITY) ? 0.f : __expf(lb - mx);
                             sum += wa + wb;
+                            const uint64_t wa2 = pack2(wa, wa), wb2 = pack2(wb, wb);
 #pragma unroll
-                            for (int r = 0; r < DP; ++r)
-                                y[r] = fmaf(wa, va[(CONVERT ? DP : 0) + r], fmaf(wb, vb[(CONVERT ? DP : 0) + r], y[r]));
+                            for (int r = 0; r < DP; r += 2) {
+                                constexpr int EO = CONVERT ? DP : 0;
+                                uint64_t yy = pack2(y[r], y[r + 1]);
+                                yy = ffma2(wb2, pack2(vb[EO + r], vb[EO + r + 1]), yy);
+                                yy = ffma2(wa2, pack2(va[EO + r], va[EO + r + 1]), yy);
+                                unpack2(yy, y[r], y[r + 1]);
+                            }
                         } else {
                             const int m = c * p.G + g;
                             if (la > mx) { second = mx; mx = la; best = m; qbest = qa; }
