@@ -18,7 +18,7 @@ using Libdl
 import Base: length, size
 
 export FrameByFrameConverter, TrajectoryConverter, GMMMapParam, GMMMap, TrajectoryGMMMap,
-       TrajectoryGVGMMMap, VarianceScaling, fvpostf, fvpostf!, diffgmm,
+       TrajectoryGVGMMMap, VarianceScaling, fvpostf, fvpostf!, diffgmm, vc_static,
        fvconvert, vc, ncomponents, dim, push_delta, align
 
 const libvcb200 = get(ENV, "LIBVCB200", joinpath(@__DIR__, "..", "libvcb200.so"))
@@ -179,6 +179,21 @@ function vc(c::TrajectoryGMMMap, fms::Vector{Matrix{Float64}})
         r = Tlast % limit
         c.T = r == 0 ? min(limit, Tlast) : r       # length of the last chunk solved (quirk Q3)
     end
+    [out[:, off[i]+1:off[i+1]] for i in 1:length(fms)]
+end
+
+# bin/vc.jl:76-82 in one call: fms hold the power row and the STATIC features only, (1+Ds, T_s); the
+# delta rows ([static; delta] per utterance, push_delta's boundary rule) are appended on the device
+function vc_static(c::TrajectoryGMMMap, fms::Vector{Matrix{Float64}})
+    limit = length(c)
+    rows = size(fms[1], 1)
+    all(m -> size(m, 1) == rows, fms) || throw(DimensionMismatch("Inconsistent dimentions."))
+    off = Int64[0; cumsum(size.(fms, 2))]
+    fm = length(fms) == 1 ? fms[1] : hcat(fms...)
+    out = Matrix{Float64}(undef, rows, size(fm, 2))
+    check(ccall((:vcb_traj_vc_static_batch, libvcb200), Int32,
+                (Ptr{Cvoid}, Ptr{Float64}, Int32, Ptr{Int64}, Int64, Int32, Ptr{Float64}),
+                c.handle, fm, rows, off, length(fms), limit, out))
     [out[:, off[i]+1:off[i+1]] for i in 1:length(fms)]
 end
 
