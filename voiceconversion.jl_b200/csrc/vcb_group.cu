@@ -123,35 +123,62 @@ __global__ void group_panel_kernel(const GroupParams p) {
     const int TI = D2p >> 2, ti = tid % TI, tf = tid / TI;     // thread tile: rows 4 ti.., frames 4 tf..
     const int i0 = 4 * ti, f0 = 4 * tf;
     const bool worker = tf < kFT / 4;
+    // element walks e -> e + nth without divisions, four loads in flight per thread
     auto load_mat = [&](const double* src) {
-        for (int e = tid; e < D2 * D2p; e += nth) {
-            const int k = e / D2p, i = e - k * D2p;
-            mat[e] = (i < D2) ? src[(size_t)m * D2 * D2 + i + (size_t)k * D2] : 0.0;
+        const double* sm_ = src + (size_t)m * D2 * D2;
+        const int dk = nth / D2p, di = nth - dk * D2p;
+        int k = tid / D2p, i = tid - k * D2p;
+        for (int e = tid; e < D2 * D2p; e += 4 * nth) {
+            double v[4];
+            int kk[4], ii[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                kk[u] = k; ii[u] = i;
+                v[u] = (e + u * nth < D2 * D2p && i < D2) ? sm_[i + (size_t)k * D2] : 0.0;
+                k += dk; i += di;
+                if (i >= D2p) { i -= D2p; ++k; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (e + u * nth < D2 * D2p) mat[(size_t)kk[u] * D2p + ii[u]] = v[u];
         }
     };
     // ---- panel
-    for (int e = tid; e < kFT * D2; e += nth) {
-        const int f = e / D2, k = e - f * D2;
-        double v = 0.0;
-        if (f < nf) {
-            const int64_t t = frames[f];
-            if (MODE == 0) {
-                v = p.X[t * p.ldx + k] - p.mux[(size_t)m * D2 + k];
-            } else {
-                const int Ds = D2 >> 1;
-                double wy;
-                if (k < Ds) {
-                    wy = p.Y[t * p.ldy + k];
-                } else {
-                    const unsigned char ed = p.edge[t];
-                    wy = 0.0;
-                    if (!(ed & 1)) wy = -0.5 * p.Y[(t - 1) * p.ldy + k - Ds];
-                    if (!(ed & 2)) wy = fma(0.5, p.Y[(t + 1) * p.ldy + k - Ds], wy);
+    {
+        const int df = nth / D2, dk = nth - df * D2;
+        int f = tid / D2, k = tid - f * D2;
+        for (int e = tid; e < kFT * D2; e += 4 * nth) {
+            double v[4];
+            int ff[4], kk[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                ff[u] = f; kk[u] = k;
+                v[u] = 0.0;
+                if (e + u * nth < kFT * D2 && f < nf) {
+                    const int64_t t = frames[f];
+                    if (MODE == 0) {
+                        v[u] = p.X[t * p.ldx + k] - p.mux[(size_t)m * D2 + k];
+                    } else {
+                        const int Ds = D2 >> 1;
+                        double wy;
+                        if (k < Ds) {
+                            wy = p.Y[t * p.ldy + k];
+                        } else {
+                            const unsigned char ed = p.edge[t];
+                            wy = 0.0;
+                            if (!(ed & 1)) wy = -0.5 * p.Y[(t - 1) * p.ldy + k - Ds];
+                            if (!(ed & 2)) wy = fma(0.5, p.Y[(t + 1) * p.ldy + k - Ds], wy);
+                        }
+                        v[u] = p.E[t * D2 + k] - wy;
+                    }
                 }
-                v = p.E[t * D2 + k] - wy;
+                f += df; k += dk;
+                if (k >= D2) { k -= D2; ++f; }
             }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (e + u * nth < kFT * D2) pan[(size_t)kk[u] * kFP + ff[u]] = v[u];
         }
-        pan[(size_t)k * kFP + f] = v;
     }
     load_mat(MODE == 0 ? p.A : p.P);
     __syncthreads();
