@@ -118,3 +118,24 @@ def test_full_c2_properties(vcb, oracle):
     assert np.abs(got - ref).max() <= tol_for(ref[1:])
     alone = vcb.vc(vcb.TrajectoryGMMMap(g, 500), np.asfortranarray(fm[:, off[333]:off[334]]))
     assert np.array_equal(alone, outs[333])
+
+
+@pytest.mark.parametrize("Ds", [1, 5, 13, 16, 23, 25, 32, 47])
+def test_static_dimensions_cover_both_solvers(vcb, oracle, Ds):
+    """Odd, padded and exact static dimensions: 1..24 run the warp-per-chunk solver (padded tiles,
+    scalar loads when Ds is odd), 25..48 the 64-thread CTA solver; the arg-max kernel pads 2Ds to 8."""
+    gm = vcb.synth.random_joint_gmm(60 + Ds, 3, 4 * Ds)
+    fm, off = vcb.synth.trajectory_utterances(gm, 3, (9, 40), 60 + Ds)
+    ref = oracle.vc_traj_batch(oracle.GMMMap(*gm), 16, fm, off)
+    t = vcb.TrajectoryGMMMap(vcb.GMMMap(*gm), 16)
+    out = np.concatenate(vcb.vc_batch(t, fm, off), axis=1)
+    assert out.shape == ref.shape and np.array_equal(out[0], fm[0])
+    assert np.abs(out - ref).max() <= tol_for(ref[1:])
+    # the static-input entry point goes through the same kernels
+    if Ds > 1:
+        stat = np.asfortranarray(fm[:1 + Ds])
+        full = np.asfortranarray(np.concatenate(
+            [np.concatenate([stat[:1, off[i]:off[i + 1]], oracle.push_delta(stat[1:, off[i]:off[i + 1]])], axis=0)
+             for i in range(3)], axis=1))
+        two = np.concatenate(vcb.vc_batch(vcb.TrajectoryGMMMap(vcb.GMMMap(*gm), 16), full, off), axis=1)
+        assert np.array_equal(vcb.vc_static_batch(vcb.TrajectoryGMMMap(vcb.GMMMap(*gm), 16), stat, off), two)
