@@ -46,13 +46,13 @@ __global__ void __launch_bounds__(kRecheckThreads)
 recheck_argmax_kernel(const double* __restrict__ X, int64_t ldx, const int* __restrict__ flag_count,
                       const int64_t* __restrict__ flag_list, const double* __restrict__ linv_cm,
                       const double* __restrict__ mux, const double* __restrict__ c, int D, int M,
-                      int32_t* __restrict__ mhat) {
+                      int32_t* __restrict__ mhat, int start) {
     extern __shared__ double xs[];  // [D]
     __shared__ double rv[kRecheckThreads / 32];
     __shared__ int ri[kRecheckThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = kRecheckThreads / 32;
     const int n = *flag_count;
-    for (int e = blockIdx.x; e < n; e += gridDim.x) {
+    for (int e = start + blockIdx.x; e < n; e += gridDim.x) {
         const int64_t t = flag_list[e];
         __syncthreads();
         for (int k = threadIdx.x; k < D; k += blockDim.x) xs[k] = X[t * ldx + k];
@@ -158,9 +158,22 @@ int32_t simt_convert(const vcb_gmmmap& g, const double* dX, int64_t T, int64_t l
 
 int32_t recheck_argmax_fp64(const vcb_gmmmap& g, const double* dX, int64_t ldx, const int* d_flag_count,
                             const int64_t* d_flag_list, int32_t* d_mhat, cudaStream_t st) {
+    // the first kPanelCap flagged frames go through the panel kernels (Linv_m staged once per 64 frames);
+    // whatever is beyond -- pathological inputs where most frames are near ties -- through the per-frame one
+    constexpr int kPanelCap = 32768;
+    static const bool per_frame = [] { const char* e = getenv("VCB_RECHECK"); return e && e[0] == 'f'; }();
+    int start = 0;
+    double* d_lout = nullptr;
+    if (!per_frame && g.D <= 256) {
+        VCB_CUDA(cudaMallocAsync((void**)&d_lout, (size_t)kPanelCap * g.M * sizeof(double), st));
+        int32_t rc = recheck_argmax_panels(g, dX, ldx, d_flag_count, d_flag_list, d_mhat, kPanelCap, d_lout, st);
+        if (rc != VCB_OK) { cudaFreeAsync(d_lout, st); return rc; }
+        start = kPanelCap;
+    }
     recheck_argmax_kernel<<<148 * 4, kRecheckThreads, g.D * sizeof(double), st>>>(
-        dX, ldx, d_flag_count, d_flag_list, g.d_linv_cm.p, g.d_mux.p, g.d_c.p, g.D, g.M, d_mhat);
+        dX, ldx, d_flag_count, d_flag_list, g.d_linv_cm.p, g.d_mux.p, g.d_c.p, g.D, g.M, d_mhat, start);
     count_launch();
+    if (d_lout) cudaFreeAsync(d_lout, st);
     VCB_CUDA(cudaGetLastError());
     return VCB_OK;
 }

@@ -234,6 +234,83 @@ __global__ void group_panel_kernel(const GroupParams p) {
     }
 }
 
+// ---- exact arg-max for the frames flagged as near ties, as panels -------------------------------
+// The flagged frames (a few per thousand) need c_m - 1/2 |Linv_m (x - mux_m)|^2 in Float64 for EVERY
+// mixture.  A block per frame streamed 64 x 18 KB of Linv from L2 per frame (L2-bandwidth bound,
+// 0.32 ms at C2); here a task is (64-frame panel of the flag list, mixture): Linv_m is staged once per
+// 64 frames.  Persistent grid, the flag count is read on the device (no host synchronisation).
+__global__ void recheck_panel_kernel(const double* __restrict__ X, int64_t ldx, const int* __restrict__ flag_count,
+                                     const int64_t* __restrict__ flag_list, const double* __restrict__ linv_cm,
+                                     const double* __restrict__ mux, const double* __restrict__ c, int D, int M,
+                                     double* __restrict__ lout, int cap) {
+    extern __shared__ __align__(16) double sm[];
+    const int Dp = (D + 3) & ~3;
+    double* mat = sm;                         // [D][Dp]  column k of Linv_m at mat + k*Dp
+    double* pan = mat + (size_t)D * Dp;       // [D][kFP]
+    double* qs = pan + (size_t)D * kFP;       // [TI][kFT] partial |z|^2 per row group (summed in a fixed order)
+    const int n = min(*flag_count, cap);
+    const int npanel = (n + kFT - 1) / kFT;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int TI = Dp >> 2, ti = tid % TI, tf = tid / TI, i0 = 4 * ti, f0 = 4 * tf;
+    const bool worker = tf < kFT / 4;
+    for (int64_t task = blockIdx.x; task < (int64_t)npanel * M; task += gridDim.x) {
+        const int pnl = (int)(task / M), m = (int)(task - (int64_t)pnl * M);
+        const int first = pnl * kFT, nf = min(kFT, n - first);
+        __syncthreads();
+        for (int e = tid; e < D * Dp; e += nth) {
+            const int k = e / Dp, i = e - k * Dp;
+            mat[e] = (i < D) ? linv_cm[(size_t)m * D * D + (size_t)k * D + i] : 0.0;
+        }
+        for (int e = tid; e < kFT * D; e += nth) {
+            const int f = e / D, k = e - f * D;
+            pan[(size_t)k * kFP + f] = (f < nf) ? X[flag_list[first + f] * ldx + k] - mux[(size_t)m * D + k] : 0.0;
+        }
+        __syncthreads();
+        if (worker) {
+            double o[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) o[r][cc] = 0.0;
+            panel_product(mat, Dp, pan, D, i0, f0, o);
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                double q = 0.0;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) q = fma(o[r][cc], o[r][cc], q);
+                qs[ti * kFT + f0 + cc] = q;
+            }
+        }
+        __syncthreads();
+        if (tid < nf) {
+            double q = 0.0;
+            for (int g = 0; g < TI; ++g) q += qs[g * kFT + tid];
+            lout[(size_t)(first + tid) * M + m] = c[m] - 0.5 * q;
+        }
+    }
+}
+
+// first maximum over the mixtures (indmax, src/gmm.jl:46); one warp per flagged frame
+__global__ void recheck_pick_kernel(const int* __restrict__ flag_count, const int64_t* __restrict__ flag_list,
+                                    const double* __restrict__ lout, int M, int cap, int32_t* __restrict__ mhat) {
+    const int n = min(*flag_count, cap);
+    const int lane = threadIdx.x & 31;
+    for (int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += gridDim.x * (blockDim.x >> 5)) {
+        double bv = -INFINITY;
+        int bi = 0x7FFFFFFF;
+        for (int m = lane; m < M; m += 32) {
+            const double l = lout[(size_t)e * M + m];
+            if (l > bv) { bv = l; bi = m; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xFFFFFFFFu, bv, o);
+            const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0 && bi != 0x7FFFFFFF) mhat[flag_list[e]] = bi;
+    }
+}
+
 }  // namespace
 
 size_t group_workspace_ints(int M, int64_t total) { return (size_t)total + 4 * (size_t)(M + 1); }
@@ -297,6 +374,26 @@ int32_t group_gv_step(const vcb_traj& tr, const int* ws, int64_t npanels, const 
     p.P = tr.d_P.p; p.D2 = g.D; p.E = const_cast<double*>(dE); p.G = dH;
     p.Y = dY; p.ldy = ldy; p.edge = d_edge;
     return launch_group(1, p, ws, g.M, npanels, st);
+}
+
+}  // namespace vcb
+
+namespace vcb {
+
+// Panel re-check of the first `cap` flagged frames; returns the scratch it used through *scratch_out so the
+// caller can free it on the stream.  Frames beyond `cap` are left to the per-frame kernel (start = cap).
+int32_t recheck_argmax_panels(const vcb_gmmmap& g, const double* dX, int64_t ldx, const int* d_flag_count,
+                              const int64_t* d_flag_list, int32_t* d_mhat, int cap, double* d_lout, cudaStream_t st) {
+    const int D = g.D, Dp = (D + 3) & ~3, TI = Dp / 4;
+    const int threads = std::min(1024, round_up(TI * (kFT / 4), 32));
+    const size_t smem = ((size_t)D * Dp + (size_t)D * kFP + (size_t)TI * kFT) * sizeof(double);
+    VCB_CUDA(cudaFuncSetAttribute(recheck_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    recheck_panel_kernel<<<148 * 3, threads, smem, st>>>(dX, ldx, d_flag_count, d_flag_list, g.d_linv_cm.p, g.d_mux.p,
+                                                        g.d_c.p, D, g.M, d_lout, cap);
+    recheck_pick_kernel<<<148, 256, 0, st>>>(d_flag_count, d_flag_list, d_lout, g.M, cap, d_mhat);
+    count_launch(); count_launch();
+    VCB_CUDA(cudaGetLastError());
+    return VCB_OK;
 }
 
 }  // namespace vcb

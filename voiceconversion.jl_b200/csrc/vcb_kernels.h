@@ -58,6 +58,10 @@ int32_t group_e_step(const vcb_traj& tr, const int* ws, int64_t npanels, const d
 int32_t group_gv_step(const vcb_traj& tr, const int* ws, int64_t npanels, const double* dY, int64_t ldy,
                       const double* dE, const unsigned char* d_edge, double* dH, cudaStream_t st);
 
+// exact arg-max of the first `cap` flagged frames as (panel, mixture) tasks; d_lout: cap * M doubles
+int32_t recheck_argmax_panels(const vcb_gmmmap& g, const double* dX, int64_t ldx, const int* d_flag_count,
+                              const int64_t* d_flag_list, int32_t* d_mhat, int cap, double* d_lout, cudaStream_t st);
+
 // ---- GV helpers (vcb_gv.cu)
 int32_t variance_scaling_device(const double* d_s2, int D, const double* dX, int64_t ldx, const int64_t* d_off,
                                 int64_t nseq, double* dY, int64_t ldy, cudaStream_t st);
