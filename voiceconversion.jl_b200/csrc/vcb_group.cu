@@ -104,8 +104,8 @@ __global__ void group_panel_kernel(const GroupParams p) {
     extern __shared__ __align__(16) double sm[];
     const int D2 = p.D2, D2p = (D2 + 3) & ~3;
     double* mat = sm;                          // [D2][D2p]  (column k at mat + k*D2p)
-    double* pan = mat + (size_t)D2 * D2p;      // [D2][kFP]  panel, row k = reduction index
-    double* mid = pan + (size_t)D2 * kFP;      // [D2][kFP]  E panel (MODE 0)
+    double* pan = mat + (size_t)D2 * D2p;      // [D2][kFP]  panel, row k = reduction index; MODE 0 overwrites it
+    double* mid = pan;                         //            with the E panel once every thread has read it
     __shared__ int s_m, s_first, s_n;
     if (threadIdx.x == 0) {
         const int tile = blockIdx.x;
@@ -193,6 +193,9 @@ __global__ void group_panel_kernel(const GroupParams p) {
                 for (int c = 0; c < 4; ++c) o[r][c] = b;
             }
             panel_product(mat, D2p, pan, D2, i0, f0, o);
+        }
+        __syncthreads();     // the x - mux panel is dead: it becomes the E panel
+        if (worker) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int f = f0 + c;
@@ -345,7 +348,7 @@ static int32_t launch_group(int mode, GroupParams& p, const int* ws, int M, int6
     const int D2p = (p.D2 + 3) & ~3, TI = D2p / 4;
     const int threads = std::min(1024, round_up(TI * (kFT / 4), 32));
     if (TI * (kFT / 4) > 1024) return fail(VCB_EUNSUPPORTED, "feature dimension %d too large for the grouped product", p.D2);
-    const size_t smem = ((size_t)p.D2 * D2p + 2 * (size_t)p.D2 * kFP) * sizeof(double);
+    const size_t smem = ((size_t)p.D2 * D2p + (size_t)p.D2 * kFP) * sizeof(double);
     if (mode == 0) {
         VCB_CUDA(cudaFuncSetAttribute(group_panel_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         group_panel_kernel<0><<<(unsigned)npanels, threads, smem, st>>>(p);
