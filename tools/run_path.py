@@ -42,7 +42,11 @@ elif which == "dtw":
     print(f"dtw C3: {ms:.3f} ms  {cells/ms*1e3:.3e} cells/s")
 elif which in ("fbf", "fbf_simt"):
     vcb.set_kernel_variant(1 if which == "fbf_simt" else 0)
-    gm, fm = vcb.synth.config_c1(int(os.environ.get("FRAMES", 1000000)))
+    if "DIM" in os.environ:     # other shapes: DIM = feature dimension, MIX = mixtures (e.g. the order-40, 32-mixture fixture shape)
+        gm = vcb.synth.random_joint_gmm(1001, int(os.environ.get("MIX", 64)), 2 * int(os.environ["DIM"]))
+        fm = vcb.synth.fbf_feature_matrix(gm, int(os.environ.get("FRAMES", 1000000)), 1001)
+    else:
+        gm, fm = vcb.synth.config_c1(int(os.environ.get("FRAMES", 1000000)))
     g = vcb.GMMMap(*gm)
     d = torch.from_numpy(np.ascontiguousarray(fm.T)).cuda()
     ms = timeit(lambda: vcb.vc(g, d))

@@ -668,7 +668,11 @@ gmm_tc_kernel(const TcParams p) {
         const int group = warp >> 2;          // with two groups: the accumulator stage this group drains
         const int row = threadIdx.x & 127;    // 0..127
         const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
-        constexpr int LOADW = (ROWS <= 64) ? ROWS : 32;   // TMEM columns fetched per wait
+        // Fast path (all of a mixture's columns in registers, stage released before the arithmetic):
+        // up to 80 columns per mixture; two mixtures at a time while both fit in the register budget.
+        constexpr bool kFast = ROWS <= 80;
+        constexpr int LOADW = kFast ? ROWS : 32;          // TMEM columns fetched per wait
+        constexpr bool kPairsHere = kEpiPairs && LOADW <= 48;
         int64_t it = 0;
         long long w_full = 0, w_part = 0, w_ld = 0, w_rel = 0, w_cmp = 0;
         const long long t_begin = clock64();
@@ -701,11 +705,11 @@ gmm_tc_kernel(const TcParams p) {
                 const uint32_t tcol = tmem_base + lane_base + (uint32_t)(acc * N);
                 if (p.debug == 4) {
                     // timing experiment: accumulators are not read
-                } else if (ROWS <= 64) {
+                } else if (kFast) {
                     // Software pipeline over the mixtures of this chunk: the TMEM loads of mixture
                     // g+1 are in flight while mixture g is reduced (tcgen05.wait::ld waits for all
                     // outstanding loads, so the wait sits after the compute).
-                    auto fetch = [&](float (&v)[LOADW], int g) {
+                    auto fetch = [&](float* v, int g) {
                         const uint32_t mcol = tcol + (uint32_t)(g * ROWS);
                         tmem_ld_cols<LOADW>(mcol, v);
                     };
@@ -716,7 +720,7 @@ gmm_tc_kernel(const TcParams p) {
                     // far inside fp32 range, and the relative accuracy of a weight does not depend
                     // on the reference point).
                     constexpr float kLazy = 40.0f;
-                    auto reduce2 = [&](const float (&va)[LOADW], const float (&vb)[LOADW], int g, bool two, float cma, float cmb) {
+                    auto reduce2 = [&](const float* va, const float* vb, int g, bool two, float cma, float cmb) {
                         // |z|^2 with packed FMAs: two 2-wide partial sums per mixture
                         uint64_t qa01 = 0ull, qa23 = 0ull, qb01 = 0ull, qb23 = 0ull;
 #pragma unroll
@@ -769,17 +773,17 @@ gmm_tc_kernel(const TcParams p) {
                     };
                     // both groups drain the same chunk: group e takes mixtures e, e + kEpiGroups, ...
                     constexpr int GS = kEpiGroups;
-                    float v0[LOADW], v1[LOADW];
+                    float v0[LOADW], v1[kPairsHere ? LOADW : 1];
                     bool released = false;
-                    for (int g = group; g < p.G; g += (kEpiPairs ? 2 : 1) * GS) {
-                        const bool two = kEpiPairs && g + GS < p.G;
+                    for (int g = group; g < p.G; g += (kPairsHere ? 2 : 1) * GS) {
+                        const bool two = kPairsHere && g + GS < p.G;
                         const float cma = cst_c[g], cmb = two ? cst_c[g + GS] : -INFINITY;   // in flight under the TMEM loads
                         const long long tl0 = p.prof ? clock64() : 0;
                         fetch(v0, g);
                         if (two) fetch(v1, g + GS);
                         tmem_ld_wait();
                         if (p.prof) w_ld += clock64() - tl0;
-                        if (g + (kEpiPairs ? 2 : 1) * GS >= p.G) {
+                        if (g + (kPairsHere ? 2 : 1) * GS >= p.G) {
                             // this group's last columns of the stage are in registers: hand the
                             // accumulator back before reducing them, so the stage is held for the
                             // TMEM read only and the MMA of chunk c+2 overlaps this arithmetic
