@@ -759,7 +759,8 @@ gmm_tc_kernel(const TcParams p) {
                             for (int r = 0; r < DP; r += 2) {
                                 constexpr int EO = CONVERT ? DP : 0;
                                 uint64_t yy = pack2(y[r], y[r + 1]);
-                                yy = ffma2(wb2, pack2(vb[EO + r], vb[EO + r + 1]), yy);
+                                // (without a second mixture vb is not loaded: 0 x garbage could be NaN)
+                                if (two) yy = ffma2(wb2, pack2(vb[EO + r], vb[EO + r + 1]), yy);
                                 yy = ffma2(wa2, pack2(va[EO + r], va[EO + r + 1]), yy);
                                 unpack2(yy, y[r], y[r + 1]);
                             }
