@@ -303,7 +303,7 @@ def main():
                                         f"bf16 {peaks.get('bf16_tflops')} TF/s, HBM {peaks.get('hbm_gbs')} GB/s {peak_src}",
                          "note": "achieved counts ALGORITHMIC flops (4MD^2+2MD per frame); the 3xTF32 split issues 3 MMAs "
                                  "per data k-step plus 1 for the offset step (K: 25 -> 80 effective), so the tensor pipe "
-                                 "executes ~3.3x that; ncu: sm__pipe_tensor_cycles_active 67%"},
+                                 "executes ~3.3x that; ncu: sm__pipe_tensor_cycles_active 69%"},
         }
 
     # ---- side measurements: trajectory (C2), DTW (C3), CPU baseline (rank 0, N=1 only)
