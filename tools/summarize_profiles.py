@@ -59,7 +59,7 @@ def launches(rnd):
     tot = sum(a[1] for a in agg.values())
     with open(os.path.join(PROF, f"{rnd}_launch_shares.txt"), "w") as f:
         f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none, command: python bench.py --steps 2 --warmup 3\n")
-        f.write("# per-launch times are cold-cache and serialised: compare SHARES, not absolutes\n")
+        f.write("# per-launch times are cold-cache and serialised: compare SHARES, not absolutes\n# (cutlass3x...tf32gemm and at::...normal_ are bench.py's own dense-TF32 peak measurement with torch.matmul, outside the timed region)\n")
         f.write(f"{'total ms':>12s} {'launches':>9s} {'share':>7s}  kernel\n")
         for n, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
             f.write(f"{t / 1e6:12.3f} {c:9d} {100 * t / tot:6.1f}%  {n}\n")
