@@ -1,24 +1,32 @@
 #!/usr/bin/env python
-"""bench.py -- converted frames/sec of the frame-by-frame GMM conversion hot path (BASELINE.json
-config C1), plus the trajectory (C2) and DTW (C3) throughputs, on N B200s of one node.
+"""bench.py -- throughput of the spectral-conversion hot path on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--path fbf|traj|dtw]
 
-One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE).  A step = one pass of
-vc(::GMMMap) over 1,000,000 synthetic 24-dim frames with a 64-mixture full-covariance joint GMM.
-Frames shard across ranks with no data-path collective ("weak": every rank converts its own 1M).
-Rank 0 prints ONE JSON line.  --impl reference times the CPU restatement of the Julia reference
-(the oracle; Julia itself is not installable in this image) on the host cores.
+One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE); rank 0 prints ONE JSON line.
+
+  --path fbf  (default; BASELINE.json configs[1], "C1")   converted frames/s of vc(::GMMMap) over
+              1,000,000 synthetic 24-dim frames with a 64-mixture full-covariance joint GMM per GPU
+              (weak scaling, no data-path collective).  The default run also carries the other
+              paths' complete sub-lines under "other_paths".
+  --path traj (configs[4], "C4")  128-mixture trajectory conversion of ONE batch of 8192 DISTINCT
+              utterances x 500 frames, sharded by utterance over the ranks with shard.shard_ragged
+              (strong scaling); the optional NCCL gather of the results is timed separately.
+  --path dtw  (configs[3], "C3")  DTW(fstep=0, bstep=2) of 1000 pairs (~600 x 600, 24-dim) per GPU.
+
+--impl reference times the CPU restatement of the Julia reference (the oracle port; Julia itself is
+not installable in this image) on the host cores, for the same path and config.
 """
 from __future__ import annotations
 
 import argparse
+import glob
 import json
 import os
+import re
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -28,9 +36,39 @@ import numpy as np  # noqa: E402
 
 M_MIX, DIM, FRAMES = 64, 24, 1_000_000
 F_FBF = 4 * M_MIX * DIM * DIM + 2 * M_MIX * DIM          # 150,528 flop/frame
-METRIC = "converted frames/sec (GMM frame-by-frame, C1)"
-WORKLOAD = ("C1: CMU-Arctic-shaped synthetic, 24-dim mcep, 64-mixture full-cov joint GMM, "
-            "frame-by-frame vc() of 1M frames per GPU")
+B_TRAJ = 48 * 24 * 24 + 24 * 24                          # 28,224 B/frame (Ds = 24)
+B_DTW = 17.0                                             # B/cell in the two-pass form
+DP_OPS_PER_CELL = 3 * 24 + 7                             # FP64 operations per DTW cell (D = 24)
+C4_UTT, C4_FRAMES, C4_MIX = 8192, 500, 128
+
+METRICS = {
+    "fbf": "converted frames/sec (GMM frame-by-frame, C1)",
+    "traj": "converted frames/sec (trajectory, C4)",
+    "dtw": "DTW cells/sec (C3)",
+}
+UNITS = {"fbf": "frames/s", "traj": "frames/s", "dtw": "cells/s"}
+
+
+def config_for(path: str, world: int) -> dict:
+    """The `config` object of a path; identical in the GPU arm and the --impl reference arm."""
+    if path == "fbf":
+        return {"workload": "C1: CMU-Arctic-shaped synthetic, 24-dim mcep, 64-mixture full-cov joint GMM, "
+                            "frame-by-frame vc() of 1M frames per GPU",
+                "frames_per_gpu": FRAMES, "mixtures": M_MIX, "dim": DIM,
+                "l2": "per-step input+output = 400 MB per GPU, larger than the 126 MB L2",
+                "parallelism": f"frames sharded over {world} GPU(s), no data-path collective"}
+    if path == "traj":
+        return {"workload": "C4: 128-mixture full-cov trajectory conversion (48-dim static+delta source) of one batch of "
+                            "8192 distinct utterances x 500 frames, one chunk per utterance",
+                "utterances": C4_UTT, "frames_per_utterance": C4_FRAMES, "mixtures": C4_MIX, "static_dim": 24,
+                "chunk_limit": C4_FRAMES,
+                "l2": "per-step input+output+factor scratch >> 126 MB L2 on every rank",
+                "parallelism": f"utterances sharded over {world} GPU(s) by shard.shard_ragged, no data-path collective; "
+                               "optional NCCL gather timed separately"}
+    return {"workload": "C3: DTW(fstep=0, bstep=2) of 1000 parallel utterance pairs (~600x600 frames, 24-dim) per GPU",
+            "pairs_per_gpu": 1000, "dim": 24, "fstep": 0, "bstep": 2,
+            "l2": "the fused kernel keeps the cost column on chip; templates + sequences + back-pointers = 0.3 GB per step",
+            "parallelism": f"pairs sharded over {world} GPU(s), no data-path collective"}
 
 
 def _env_int(name, default):
@@ -110,21 +148,25 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(kernel_file: str):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the
-    latest `ncu --set full` summary committed under profiles/ (None if there is none)."""
-    import glob
-    import re
+def ncu_summary(kernel_file: str):
+    """Metrics of the dominant kernel from the latest `ncu --set full` summary committed under
+    profiles/ (tools/summarize_profiles.py): DRAM traffic per launch and pipe utilisations."""
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_{kernel_file}.txt")))
+    out = {"traffic": None, "source": None}
     if not files:
-        return None, None
+        return out
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     tot = 0.0
     for line in open(files[-1]):
         m = re.match(r"dram__bytes_(read|write)\.sum\s+([0-9.]+)\s+(\w+)", line)
         if m:
             tot += float(m.group(2)) * unit.get(m.group(3), 1.0)
-    return (tot or None), os.path.relpath(files[-1], ROOT)
+        m = re.match(r"(sm__pipe_fp64_cycles_active|sm__pipe_tensor_cycles_active|sm__warps_active|launch__grid_size)\S*\s+([0-9.]+)", line)
+        if m:
+            out[m.group(1)] = float(m.group(2))
+    out["traffic"] = tot or None
+    out["source"] = os.path.relpath(files[-1], ROOT)
+    return out
 
 
 def measure_tf32_peak(torch):
@@ -147,38 +189,397 @@ def measure_tf32_peak(torch):
         torch.backends.cuda.matmul.allow_tf32 = old
 
 
-def cpu_reference_arm(args):
-    """--impl reference: the CPU restatement of the Julia reference (oracle port) on all host cores."""
-    rank = _env_int("RANK", 0)
-    if rank != 0:
-        return
+def dtw_pairs_for_rank(vcb, rank: int):
+    """1000 C3 pairs; rank r aligns its own, distinct set (seed 1003 + r)."""
+    return vcb.synth.config_c3(1000, seed=1003 + rank)
+
+
+# ------------------------------------------------------------------------------------------------
+# --impl reference: the CPU restatement of the Julia reference (oracle port) on all host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_run(path: str, steps: int, warmup: int, cores: int):
+    """Times `steps` passes of the oracle over (a bounded sample of) the path's workload.
+    Returns (units per second, seconds per step, sample description)."""
     import vcb200 as vcb
     from oracle import oracle as O
     O.build()
-    cores = host_cores()
-    sample = 25_000 * max(cores, 1)
-    sample = min(sample, 400_000)
-    gm, fm = vcb.synth.config_c1(sample)
-    g = O.GMMMap(*gm)
-    for _ in range(max(args.warmup, 1)):
-        g.vc(np.asfortranarray(fm[:, : sample // 8]), nthreads=cores)
+    if path == "fbf":
+        gm, fm = vcb.synth.config_c1(FRAMES)
+        g = O.GMMMap(*gm)
+        units, what = FRAMES, (f"all {FRAMES} frames of the C1 workload per step, OpenMP over frames on {cores} threads; C "
+                               "restatement of the Julia reference (Julia 0.5 is not installable here and is single-threaded)")
+        run = lambda: g.vc(fm, nthreads=cores)                                     # noqa: E731
+        warm = lambda: g.vc(np.asfortranarray(fm[:, : FRAMES // 16]), nthreads=cores)   # noqa: E731
+    elif path == "traj":
+        n = min(C4_UTT, 8 * cores)
+        gm = vcb.synth.random_joint_gmm(1004, C4_MIX, 96)
+        fm, off = vcb.synth.c4_utterances(gm, np.arange(n), C4_FRAMES)
+        g = O.GMMMap(*gm)
+        units, what = n * C4_FRAMES, (f"utterances 0..{n - 1} of the C4 batch ({n} x {C4_FRAMES} frames) per step, OpenMP over "
+                                      f"utterances on {cores} threads; C restatement of the Julia reference")
+        run = lambda: O.vc_traj_batch(g, C4_FRAMES, fm, off, nthreads=cores)       # noqa: E731
+        warm = lambda: O.vc_traj_batch(g, C4_FRAMES, np.asfortranarray(fm[:, : off[cores]]), off[: cores + 1], nthreads=cores)  # noqa: E731
+    else:
+        tm, to, sq, so = dtw_pairs_for_rank(vcb, 0)
+        units = float(np.sum(np.diff(to).astype(np.float64) * np.diff(so)))
+        what = (f"all 1000 pairs of the C3 workload per step, OpenMP over pairs on {cores} threads; C restatement of the "
+                "Julia reference")
+        run = lambda: O.dtw_fit_batch(tm, to, sq, so, 0, 2, nthreads=cores)        # noqa: E731
+        warm = lambda: O.dtw_fit_batch(tm, to[:65], sq, so[:65], 0, 2, nthreads=cores)  # noqa: E731
+    for _ in range(max(warmup, 1)):
+        warm()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        g.vc(fm, nthreads=cores)
-    dt = time.perf_counter() - t0
-    value = sample * args.steps / dt
+    for _ in range(steps):
+        run()
+    dt = (time.perf_counter() - t0) / steps
+    return units / dt, dt, what
+
+
+def cpu_reference_arm(args):
+    if _env_int("RANK", 0) != 0:
+        return
+    cores = host_cores()
+    value, dt, what = cpu_run(args.path, args.steps, args.warmup, cores)
+    unit = UNITS[args.path]
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU arm: each step is a bounded sample of the workload"},
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} frames of the C1 workload per step, OpenMP over frames; C restatement "
-                                   "of the Julia reference (Julia 0.5 is not installable here)"},
-        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRICS[args.path], "value": value, "unit": unit, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong" if args.path == "traj" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_for(args.path, args.gpus),
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": what},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(path: str) -> dict:
+    """cpu_baseline object of the GPU arm (rank 0, N = 1): one bounded pass of the oracle."""
+    unit = UNITS[path]
+    try:
+        cores = host_cores()
+        if path == "fbf":
+            # a bounded slice of the 1M frames keeps the default run short
+            import vcb200 as vcb
+            from oracle import oracle as O
+            O.build()
+            gm, fm = vcb.synth.config_c1(FRAMES)
+            sample = min(FRAMES, 25_000 * cores)
+            og = O.GMMMap(*gm)
+            sub = np.asfortranarray(fm[:, :sample])
+            og.vc(np.asfortranarray(sub[:, : sample // 10]), nthreads=cores)
+            t0 = time.perf_counter(); og.vc(sub, nthreads=cores); dt_all = time.perf_counter() - t0
+            n1 = min(sample, 20_000)
+            t0 = time.perf_counter(); og.vc(np.asfortranarray(sub[:, :n1])); dt_1 = time.perf_counter() - t0
+            return {"value": sample / dt_all, "unit": unit, "cores": cores, "kind": "port",
+                    "sample": f"first {sample} frames of the same C1 workload, OpenMP over frames (C restatement of the "
+                              "Julia reference; Julia is single-threaded)",
+                    "single_thread_value": n1 / dt_1, "single_thread_sample": f"first {n1} frames"}
+        value, _, what = cpu_run(path, 1, 1, cores)
+        return {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": what}
+    except Exception as ex:
+        return {"value": None, "unit": unit, "cores": 0, "kind": "port", "sample": repr(ex)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class Ctx:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        import vcb200 as vcb
+        self.torch, self.dist, self.vcb, self.args = torch, dist, vcb, args
+        self.rank, self.world, self.local = _env_int("RANK", 0), _env_int("WORLD_SIZE", 1), _env_int("LOCAL_RANK", 0)
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a B200: no CUDA device is visible and there is no CPU path")
+        torch.cuda.set_device(self.local)
+        vcb.set_device(self.local)
+        vcb.set_kernel_variant(args.variant)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.peaks, self.peak_src = measured_peaks()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def timed(self, fn, steps: int, warmup: int, stage_index=None):
+        """W untimed + K timed calls of fn() bracketed by barrier + synchronize; CUDA events on the
+        current stream (the stream the library launches on).  Returns (ms per step as the max over
+        ranks, launches, mean duration of stage `stage_index` of the library's stage marks)."""
+        torch, vcb = self.torch, self.vcb
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        l0 = vcb.launch_count()
+        if stage_index is not None:
+            vcb.stage_timing(True)      # the library records CUDA events between its stages, per call
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        self.barrier()
+        stages = []
+        if stage_index is not None:
+            stages = vcb.stage_times()      # mean over the timed steps (the last 64 at most)
+            vcb.stage_timing(False)
+        launches = vcb.launch_count() - l0
+        ms = self.max_over_ranks(s.elapsed_time(e) / steps)
+        return ms, int(launches), (stages[stage_index] if len(stages) > (stage_index or 0) else None), stages
+
+    def pinned(self, arr_T):
+        """(rows, T) column-major numpy view of a page-locked copy of arr_T (T, rows)."""
+        t = self.torch.from_numpy(np.ascontiguousarray(arr_T)).pin_memory()
+        return t, t.numpy().T
+
+
+def run_fbf(ctx: Ctx, steps: int, warmup: int) -> dict:
+    torch, vcb, args = ctx.torch, ctx.vcb, ctx.args
+    T = args.frames
+    gm, fm = vcb.synth.config_c1(T)                 # same seeded inputs on every rank (weak scaling)
+    g = vcb.GMMMap(*gm)
+    rows = fm.shape[0]
+    dfm = torch.from_numpy(np.ascontiguousarray(fm.T)).cuda()   # frame-major (T, rows) == Julia's (rows, T)
+    in_bytes = dfm.numel() * 8
+    out = [None]
+
+    def step():
+        out[0] = vcb.vc(g, dfm)
+    # one kernel per step: the step time is the kernel time
+    ms, launches, _, _ = ctx.timed(step, steps, warmup)
+    value = ctx.world * T / (ms * 1e-3)
+
+    # end to end through the public host API: pinned host buffers, H2D + D2H inside the timed region
+    _, hfm = ctx.pinned(fm.T)
+    hout_t = torch.empty((T, rows), dtype=torch.float64).pin_memory()
+    hout = hout_t.numpy().T
+    e2e_steps = max(3, min(steps, 10))
+    for _ in range(2):
+        vcb.vc(g, hfm, out=hout)
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        vcb.vc(g, hfm, out=hout)
+    torch.cuda.synchronize()
+    e2e_s = ctx.max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    e2e_ok = bool(np.array_equal(hout[0], fm[0]))
+    if ctx.rank != 0:
+        return {}
+    tf32_peak = measure_tf32_peak(torch)
+    achieved = F_FBF * T / (ms * 1e-3) / 1e12
+    used_tc = args.variant != 1
+    prof = ncu_summary("prof_fbf_tc" if used_tc else "prof_fbf_simt")
+    cfg = config_for("fbf", ctx.world)
+    cfg["frames_per_gpu"] = T
+    cfg["kernel"] = "tcgen05 3xTF32 (gmm_tc_kernel)" if used_tc else "CUDA-core fp32 (gmm_simt_kernel)"
+    return {
+        "metric": METRICS["fbf"], "value": value, "unit": "frames/s", "n_gpus": ctx.world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "tf32x3 (fp32-accurate tensor-core split; f64 API)" if used_tc else "f32", "data": "synthetic",
+        "config": cfg,
+        "e2e": {"value": ctx.world * T / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": in_bytes,
+                "d2h_bytes_per_step": in_bytes, "steps": e2e_steps, "power_row_ok": e2e_ok,
+                "note": "vc(g, fm) through the C ABI with pinned Float64 host buffers, pipelined H2D/kernel/D2H"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+                     "frac": achieved / tf32_peak, "traffic": prof["traffic"],
+                     "traffic_unit": "bytes/launch (DRAM read+write, ncu)", "traffic_source": prof["source"],
+                     "kernel": "gmm_tc_kernel<24,true>" if used_tc else "gmm_simt_kernel<24,2,true>",
+                     "kernel_ms": ms, "algorithmic_flop_per_frame": F_FBF,
+                     "peak_source": "dense TF32 measured in this run (torch.matmul 8192^3, best of 10); "
+                                    f"bf16 {ctx.peaks.get('bf16_tflops')} TF/s, HBM {ctx.peaks.get('hbm_gbs')} GB/s {ctx.peak_src}",
+                     "note": "achieved counts ALGORITHMIC flops (4MD^2+2MD per frame); the 3xTF32 split issues 3 MMAs "
+                             "per data k-step plus 1 for the offset step (K: 25 -> 80 effective), so the tensor pipe "
+                             "executes ~3.3x that; ncu: sm__pipe_tensor_cycles_active "
+                             f"{prof.get('sm__pipe_tensor_cycles_active')} %"},
+    }
+
+
+_CACHE: dict = {}
+
+
+def run_traj(ctx: Ctx, steps: int, warmup: int, which: str = "c4", limit: int = 500) -> dict:
+    """which = "c4": the 8192-utterance batch sharded over the ranks (strong scaling, the --path traj
+    line); "c2": 1000 utterances x 500 frames with 64 mixtures per GPU (side number)."""
+    torch, vcb = ctx.torch, ctx.vcb
+    if which == "c4":
+        gm = vcb.synth.random_joint_gmm(1004, C4_MIX, 96)
+        all_off = np.arange(C4_UTT + 1, dtype=np.int64) * C4_FRAMES
+        (ub, ue), off = vcb.shard.shard_ragged(all_off, ctx.rank, ctx.world)
+        fm, off = vcb.synth.c4_utterances(gm, np.arange(ub, ue), C4_FRAMES)     # this rank's own utterances
+        total_frames = C4_UTT * C4_FRAMES
+        cfg = config_for("traj", ctx.world)
+        cfg["chunk_limit"] = limit
+    else:
+        if "c2" not in _CACHE:
+            _CACHE["c2"] = vcb.synth.config_c2(1000, 500)
+        gm, fm, off = _CACHE["c2"]
+        ub, ue = 0, 1000
+        total_frames = ctx.world * 1000 * 500
+        cfg = {"workload": "C2: 48-dim source (static+delta), 64 mixtures, 1000 utt x 500 frames per GPU, chunk limit "
+                           f"{limit}" + (" (the CLI default, bin/vc.jl:18)" if limit == 100 else " (one chunk per utterance)"),
+               "chunk_limit": limit}
+    local_frames = int(off[-1])
+    tj = vcb.TrajectoryGMMMap(vcb.GMMMap(*gm), limit)
+    dfm = torch.from_numpy(np.ascontiguousarray(fm.T)).cuda()
+    out = [None]
+
+    def step():
+        out[0], = vcb.vc_batch(tj, dfm, off, _split=False)
+    ms, launches, solver_ms, stages = ctx.timed(step, steps, warmup, stage_index=3)
+    vcb.traj_status(tj)
+    value = total_frames / (ms * 1e-3)
+
+    gather = None
+    if which == "c4" and ctx.world > 1:
+        # optional result gather (SURVEY 8e), timed separately from the conversion
+        sizes = [int(np.diff(vcb.shard.shard_ragged(all_off, r, ctx.world)[0])[0]) * C4_FRAMES for r in range(ctx.world)]
+        for _ in range(2):
+            vcb.shard.gather_frames(out[0], ctx.dist, sizes=sizes)
+        ctx.barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(5):
+            full = vcb.shard.gather_frames(out[0], ctx.dist, sizes=sizes)
+        e.record(); ctx.barrier()
+        gms = ctx.max_over_ranks(s.elapsed_time(e) / 5)
+        gather = {"ms": gms, "bytes_to_rank0": (total_frames - local_frames) * 25 * 8 if ctx.rank == 0 else None,
+                  "gbs_into_rank0": (total_frames - local_frames) * 25 * 8 / (gms * 1e-3) / 1e9 if ctx.rank == 0 else None,
+                  "how": "shard.gather_frames: ncclSend/ncclRecv of each rank's (frames, 25) result into rank 0's "
+                         "preallocated batch over NVLink/NVSwitch"}
+        if ctx.rank == 0:
+            gather["rows_ok"] = bool(full is not None and full.shape[0] == total_frames)
+        del full
+
+    # end to end: host Float64 buffers through vcb_traj_vc_batch (H2D + kernels + D2H, sliced pipeline)
+    _, hfm = ctx.pinned(fm.T)
+    hout_t = torch.empty((local_frames, 25), dtype=torch.float64).pin_memory()
+    hout = hout_t.numpy().T
+    e2e_steps = 3
+    for _ in range(2):
+        vcb.vc_batch(tj, hfm, off, _split=False, out=hout)
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        vcb.vc_batch(tj, hfm, off, _split=False, out=hout)
+    torch.cuda.synchronize()
+    e2e_s = ctx.max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    h2d = ctx.sum_over_ranks(float(hfm.size * 8)) / ctx.world
+    d2h = ctx.sum_over_ranks(float(hout.size * 8)) / ctx.world
+    dev = out[0].cpu().numpy().T
+    same = bool(np.array_equal(dev, hout)) and bool(np.array_equal(hout[0], fm[0]))
+    if ctx.rank != 0:
+        return {}
+    hbm = ctx.peaks.get("hbm_gbs", 6650.0)
+    prof = ncu_summary("prof_traj")
+    kms = solver_ms if solver_ms else ms
+    achieved = B_TRAJ * local_frames / (kms * 1e-3) / 1e9
+    return {
+        "metric": METRICS["traj"] if which == "c4" else "converted frames/sec (trajectory, C2)",
+        "value": value, "unit": "frames/s", "n_gpus": ctx.world, "steps": steps, "warmup": warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong" if which == "c4" else "weak", "vs_baseline": None,
+        "dtype": "f64 (band solve, E/PE) + tf32x3 arg-max with f64 re-check", "data": "synthetic",
+        "config": cfg,
+        "shard": {"rank0_utterances": [int(ub), int(ue)], "rank0_frames": local_frames},
+        "stages_ms": {"argmax_recheck": stages[0] if len(stages) > 0 else None, "bucketing": stages[1] if len(stages) > 1 else None,
+                      "e_pe_panels": stages[2] if len(stages) > 2 else None, "band_solver": solver_ms},
+        "gather": gather,
+        "e2e": {"value": total_frames / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "steps": e2e_steps, "matches_device_path": same,
+                "note": "vc(c, fms) batch through vcb_traj_vc_batch with pinned Float64 host buffers; utterance slices of "
+                        "one solver wave rotate through streams (bytes are the per-rank average)"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                     "traffic": (prof["traffic"] / (prof["launch__grid_size"] * 500.0) * local_frames
+                                 if prof["traffic"] and prof.get("launch__grid_size") else None),
+                     "traffic_unit": "bytes/launch (DRAM read+write; ncu capture of a 500-frame-per-chunk launch, scaled by "
+                                     "frames to this launch)",
+                     "traffic_source": prof["source"], "kernel": "traj_solve_warp<3,true>", "kernel_ms": kms,
+                     "algorithmic_bytes_per_frame": B_TRAJ, "frames_per_launch": local_frames,
+                     "step_frac": B_TRAJ * local_frames / (ms * 1e-3) / 1e9 / hbm,
+                     "peak_source": f"HBM copy bandwidth {ctx.peak_src}",
+                     "note": "achieved = 28,224 B/frame (SURVEY 8d: L written + read once, E read, y written) x frames of "
+                             "one launch / the band solver's own duration (CUDA events around the kernel inside the timed "
+                             "region); step_frac divides by the whole step (arg-max + E/PE + solver) instead. The solver "
+                             "stores only Linv_t and L[t][t-1] (15,360 B/frame), so its real DRAM traffic is below the "
+                             f"algorithmic figure; ncu: warps active {prof.get('sm__warps_active')} %, "
+                             f"FP64/DMMA pipe {prof.get('sm__pipe_fp64_cycles_active')} %"},
+    }
+
+
+def run_dtw(ctx: Ctx, steps: int, warmup: int) -> dict:
+    torch, vcb = ctx.torch, ctx.vcb
+    tm, to, sq, so = dtw_pairs_for_rank(vcb, ctx.rank)
+    dtm = torch.from_numpy(np.ascontiguousarray(tm.T)).cuda()
+    dsq = torch.from_numpy(np.ascontiguousarray(sq.T)).cuda()
+    d = vcb.DTWs.DTW(fstep=0, bstep=2)
+    cells = float(np.sum(np.diff(to).astype(np.float64) * np.diff(so)))
+    res = [None]
+
+    def step():
+        res[0] = vcb.DTWs.fit_batch(d, dtm, to, dsq, so)
+    ms, launches, kernel_ms, _ = ctx.timed(step, steps, warmup, stage_index=1)
+    total_cells = ctx.sum_over_ranks(cells)
+    value = total_cells / (ms * 1e-3)
+
+    # end to end: host arrays through vcb_dtw_fit_batch
+    _, htm = ctx.pinned(tm.T)
+    _, hsq = ctx.pinned(sq.T)
+    vcb.DTWs.fit_batch(d, htm, to, hsq, so)
+    ctx.barrier()
+    e2e_steps = 5
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        hp, hc = vcb.DTWs.fit_batch(d, htm, to, hsq, so)
+    e2e_s = ctx.max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    same = bool(np.array_equal(res[0][0].cpu().numpy(), hp))
+    if ctx.rank != 0:
+        return {}
+    hbm = ctx.peaks.get("hbm_gbs", 6650.0)
+    prof = ncu_summary("prof_dtw")
+    kms = kernel_ms if kernel_ms else ms
+    achieved = B_DTW * cells / (kms * 1e-3) / 1e9
+    sm_clock = (ctx.peaks.get("sm_max_mhz") or 1965.0) * 1e6
+    fp64_floor_ms = DP_OPS_PER_CELL * cells / (64.0 * 148 * sm_clock) * 1e3
+    return {
+        "metric": METRICS["dtw"], "value": value, "unit": "cells/s", "n_gpus": ctx.world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (bit-exact)",
+        "data": "synthetic", "config": config_for("dtw", ctx.world),
+        "e2e": {"value": total_cells / e2e_s, "unit": "cells/s", "h2d_bytes_per_step": int((tm.size + sq.size) * 8),
+                "d2h_bytes_per_step": int(hp.size * 8 + hc.size * 8), "steps": e2e_steps, "matches_device_path": same,
+                "note": "DTWs.fit_batch through vcb_dtw_fit_batch with pinned Float64 host buffers"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                     "traffic": prof["traffic"], "traffic_unit": "bytes/launch (DRAM read+write, ncu)",
+                     "traffic_source": prof["source"], "kernel": "dtw_fused_kernel", "kernel_ms": kms,
+                     "algorithmic_bytes_per_cell": B_DTW, "cells_per_launch": cells,
+                     "peak_source": f"HBM copy bandwidth {ctx.peak_src}",
+                     "fp64_pipe": {"dp_ops_per_cell": DP_OPS_PER_CELL, "floor_ms": fp64_floor_ms, "frac_of_floor": fp64_floor_ms / kms,
+                                   "ncu_pipe_fp64_active_pct": prof.get("sm__pipe_fp64_cycles_active"),
+                                   "note": "64 FP64 lanes/clk/SM x 148 SMs at the maximum SM clock"},
+                     "note": "achieved uses SURVEY 8d's 17 B/cell of the two-pass form (cost matrix written + read, 1 B "
+                             "back-pointer); the kernel is fused (cost matrix never leaves the SM), so the real bound "
+                             "is the FP64 pipe: see fp64_pipe"},
+    }
 
 
 def main():
@@ -187,8 +588,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=FRAMES, help="frames per GPU per step (default: the C1 size)")
-    ap.add_argument("--skip-extras", action="store_true", help="skip the C2/C3/CPU-baseline side measurements")
+    ap.add_argument("--path", default="fbf", choices=["fbf", "traj", "dtw"])
+    ap.add_argument("--frames", type=int, default=FRAMES, help="frames per GPU per step (fbf; default: the C1 size)")
+    ap.add_argument("--skip-extras", action="store_true", help="fbf: skip the other paths' sub-lines and the CPU baseline")
     ap.add_argument("--variant", type=int, default=0, help="0 auto, 1 CUDA-core kernel, 2 tcgen05 kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -197,201 +599,49 @@ def main():
         cpu_reference_arm(args)
         return
 
-    import torch
-    import torch.distributed as dist
-    import vcb200 as vcb
-
-    rank, world, local = _env_int("RANK", 0), _env_int("WORLD_SIZE", 1), _env_int("LOCAL_RANK", 0)
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200: no CUDA device is visible and there is no CPU path")
-    torch.cuda.set_device(local)
-    vcb.set_device(local)
-    vcb.set_kernel_variant(args.variant)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    T = args.frames
-    gm, fm = vcb.synth.config_c1(T)                 # same seeded inputs on every rank (weak scaling)
-    g = vcb.GMMMap(*gm)
-    rows = fm.shape[0]
-    # frame-major device tensor (T, rows) == Julia's (rows, T) memory
-    dfm = torch.from_numpy(np.ascontiguousarray(fm.T)).cuda()
-    in_bytes = dfm.numel() * 8
-
-    # ---- device-resident timing (value): inputs already in HBM, 2 x 200 MB per step >> 126 MB L2
-    sampler = ClockSampler(local)
-    if rank == 0:
+    ctx = Ctx(args)
+    sampler = ClockSampler(ctx.local)
+    if ctx.rank == 0:
         sampler.start()       # samples cover warm-up, the timed device loop and the end-to-end loop
-    for _ in range(args.warmup):
-        out = vcb.vc(g, dfm)
-    barrier()
-    l0 = vcb.launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    barrier()
-    ev[0].record()
-    for i in range(args.steps):
-        out = vcb.vc(g, dfm)
-        ev[i + 1].record()
-    barrier()
-    launches = vcb.launch_count() - l0
-    total_ms = ev[0].elapsed_time(ev[-1])
-    kern_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    total_ms = max_over_ranks(total_ms)
-    ms_per_step = total_ms / args.steps
-    value = world * T / (ms_per_step * 1e-3)
+    if args.path == "fbf":
+        line = run_fbf(ctx, args.steps, args.warmup)
+    elif args.path == "traj":
+        line = run_traj(ctx, args.steps, args.warmup, "c4", C4_FRAMES)
+    else:
+        line = run_dtw(ctx, args.steps, args.warmup)
+    clocks = sampler.stop() if ctx.rank == 0 else None
+    if ctx.rank == 0:
+        line["clocks"] = clocks
 
-    # ---- end to end through the public host API: pinned host buffers, H2D + D2H inside the timed region
-    hfm_t = torch.from_numpy(np.ascontiguousarray(fm.T)).pin_memory()
-    hfm = hfm_t.numpy().T                           # (rows, T) column-major view of pinned memory
-    hout_t = torch.empty((T, rows), dtype=torch.float64).pin_memory()
-    hout = hout_t.numpy().T
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        vcb.vc(g, hfm, out=hout)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        vcb.vc(g, hfm, out=hout)
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
-    e2e_value = world * T / e2e_s
-    clocks = sampler.stop() if rank == 0 else None
-    e2e_ok = bool(np.array_equal(hout[0], fm[0]))
-
-    line = None
-    if rank == 0:
-        peaks, peak_src = measured_peaks()
-        tf32_peak = measure_tf32_peak(torch)
-        kernel_ms = float(np.mean(kern_ms))
-        achieved = F_FBF * T / (kernel_ms * 1e-3) / 1e12
-        used_tc = args.variant != 1
-        traffic, traffic_src = ncu_traffic("prof_fbf_tc" if used_tc else "prof_fbf_simt")
-        line = {
-            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "tf32x3 (fp32-accurate tensor-core split; f64 API)" if used_tc else "f32",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_gpu": T, "mixtures": M_MIX, "dim": DIM,
-                       "l2": "per-step input+output = %.0f MB per GPU, larger than the 126 MB L2" % (2 * in_bytes / 1e6),
-                       "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
-                       "kernel": "tcgen05 3xTF32 (gmm_tc_kernel)" if used_tc else "CUDA-core fp32 (gmm_simt_kernel)"},
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": in_bytes,
-                    "steps": e2e_steps, "power_row_ok": e2e_ok,
-                    "note": "vc(g, fm) through the C ABI with pinned Float64 host buffers, pipelined H2D/kernel/D2H"},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                         "frac": achieved / tf32_peak, "traffic": traffic, "traffic_unit": "bytes/launch (DRAM read+write, ncu)",
-                         "traffic_source": traffic_src,
-                         "kernel": "gmm_tc_kernel<24,true>" if used_tc else "gmm_simt_kernel<24,2,true>",
-                         "kernel_ms": kernel_ms,
-                         "algorithmic_flop_per_frame": F_FBF,
-                         "peak_source": "dense TF32 measured in this run (torch.matmul 8192^3, best of 10); "
-                                        f"bf16 {peaks.get('bf16_tflops')} TF/s, HBM {peaks.get('hbm_gbs')} GB/s {peak_src}",
-                         "note": "achieved counts ALGORITHMIC flops (4MD^2+2MD per frame); the 3xTF32 split issues 3 MMAs "
-                                 "per data k-step plus 1 for the offset step (K: 25 -> 80 effective), so the tensor pipe "
-                                 "executes ~3.3x that; ncu: sm__pipe_tensor_cycles_active 69%"},
-        }
-
-    # ---- side measurements: trajectory (C2), DTW (C3), CPU baseline (rank 0, N=1 only)
-    if not args.skip_extras:
+    # the other paths' complete sub-lines (same structure as a contract line), default run only
+    if args.path == "fbf" and not args.skip_extras:
         extras = {}
-        try:
-            n_utt = 1000
-            gm2, fm2, off2 = vcb.synth.config_c2(n_utt, 500)
-            tj = vcb.TrajectoryGMMMap(vcb.GMMMap(*gm2), 500)
-            dfm2 = torch.from_numpy(np.ascontiguousarray(fm2.T)).cuda()
-            for _ in range(2):
-                vcb.vc_batch(tj, dfm2, off2, _split=False)
-            barrier()
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            for _ in range(3):
-                vcb.vc_batch(tj, dfm2, off2, _split=False)
-            e.record(); barrier()
-            ms = max_over_ranks(s.elapsed_time(e) / 3)
-            fr = n_utt * 500
-            b_traj = 48 * 24 * 24 + 24 * 24            # B/frame
-            extras["trajectory_c2"] = {"value": world * fr / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms,
-                                       "workload": "C2: 48-dim source (static+delta), 64 mixtures, 1000 utt x 500 frames, one chunk per utterance",
-                                       "hbm_equiv_gbs": b_traj * fr / (ms * 1e-3) / 1e9}
-            del dfm2
-            # C4's per-GPU shard: 128 mixtures, 1024 utterances x 500 frames (8192 utterances on 8 GPUs)
-            gm4, fm4, off4 = vcb.synth.config_c2(1024, 500, M=128, seed=1004)
-            tj4 = vcb.TrajectoryGMMMap(vcb.GMMMap(*gm4), 500)
-            dfm4 = torch.from_numpy(np.ascontiguousarray(fm4.T)).cuda()
-            for _ in range(2):
-                vcb.vc_batch(tj4, dfm4, off4, _split=False)
-            barrier()
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            for _ in range(3):
-                vcb.vc_batch(tj4, dfm4, off4, _split=False)
-            e.record(); barrier()
-            ms = max_over_ranks(s.elapsed_time(e) / 3)
-            extras["trajectory_c4_shard"] = {"value": world * 1024 * 500 / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms,
-                                             "workload": "C4 shard: 128 mixtures, 1024 utt x 500 frames per GPU",
-                                             "hbm_equiv_gbs": b_traj * 1024 * 500 / (ms * 1e-3) / 1e9}
-            del dfm4, fm4
-            tm, to, sq, so = vcb.synth.config_c3(1000)
-            dtm = torch.from_numpy(np.ascontiguousarray(tm.T)).cuda(); dsq = torch.from_numpy(np.ascontiguousarray(sq.T)).cuda()
-            d = vcb.DTWs.DTW(fstep=0, bstep=2)
-            for _ in range(2):
-                vcb.DTWs.fit_batch(d, dtm, to, dsq, so)
-            barrier()
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            for _ in range(3):
-                vcb.DTWs.fit_batch(d, dtm, to, dsq, so)
-            e.record(); barrier()
-            ms = max_over_ranks(s.elapsed_time(e) / 3)
-            cells = float(np.sum(np.diff(to).astype(np.float64) * np.diff(so)))
-            extras["dtw_c3"] = {"value": world * cells / (ms * 1e-3), "unit": "cells/s", "ms_per_step": ms,
-                                "workload": "C3: 1000 pairs, ~600x600 frames, 24-dim, DTW(fstep=0,bstep=2)",
-                                "hbm_equiv_gbs": 17.0 * cells / (ms * 1e-3) / 1e9}
-        except Exception as ex:  # side numbers must never break the contract line
-            extras["error"] = repr(ex)
-        if rank == 0:
+        side_steps = max(3, min(args.steps, 5))
+        for name, fn in (("trajectory_c4", lambda: run_traj(ctx, side_steps, 3, "c4", C4_FRAMES)),
+                         ("trajectory_c2", lambda: run_traj(ctx, side_steps, 3, "c2", 500)),
+                         ("trajectory_c2_limit100", lambda: run_traj(ctx, side_steps, 3, "c2", 100)),
+                         ("dtw_c3", lambda: run_dtw(ctx, side_steps, 3))):
+            try:
+                extras[name] = fn()
+            except Exception as ex:  # side numbers must never break the contract line
+                extras[name] = {"error": repr(ex)}
+                ctx.torch.cuda.synchronize()
+        if ctx.rank == 0:
+            if ctx.world == 1:
+                for name, path in (("trajectory_c4", "traj"), ("dtw_c3", "dtw")):
+                    if "error" not in extras[name]:
+                        extras[name]["cpu_baseline"] = cpu_baseline(path)
             line["other_paths"] = extras
-            if world == 1:
-                try:
-                    from oracle import oracle as O
-                    O.build()
-                    cores = host_cores()
-                    sample = min(T, 25_000 * cores)
-                    og = O.GMMMap(*gm)
-                    sub = np.asfortranarray(fm[:, :sample])
-                    og.vc(np.asfortranarray(sub[:, : sample // 10]), nthreads=cores)
-                    t0 = time.perf_counter(); og.vc(sub, nthreads=cores); dt_all = time.perf_counter() - t0
-                    n1 = min(sample, 20_000)
-                    t0 = time.perf_counter(); og.vc(np.asfortranarray(sub[:, :n1])); dt_1 = time.perf_counter() - t0
-                    line["cpu_baseline"] = {"value": sample / dt_all, "unit": "frames/s", "cores": cores, "kind": "port",
-                                            "sample": f"first {sample} frames of the same C1 workload, OpenMP over frames "
-                                                      "(C restatement of the Julia reference; Julia is single-threaded)",
-                                            "single_thread_value": n1 / dt_1, "single_thread_sample": f"first {n1} frames"}
-                except Exception as ex:
-                    line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port", "sample": repr(ex)}
-    if rank == 0:
-        if "cpu_baseline" not in line:
-            line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "port",
+    if ctx.rank == 0:
+        if ctx.world == 1 and not (args.path == "fbf" and args.skip_extras):
+            line["cpu_baseline"] = cpu_baseline(args.path)
+        else:
+            line["cpu_baseline"] = {"value": None, "unit": UNITS[args.path], "cores": 0, "kind": "port",
                                     "sample": "not measured in this run (N>1 or --skip-extras)"}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    if ctx.world > 1:
+        ctx.dist.barrier()
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

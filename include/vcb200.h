@@ -68,6 +68,16 @@ int32_t vcb_set_kernel_variant(int32_t variant);
 /* Number of kernel launches issued by this library since process start (bench bookkeeping). */
 int64_t vcb_launch_count(void);
 
+/* Profiling aid for bench.py: when enabled, the trajectory and DTW device paths record CUDA events
+ * between their stages on the caller's stream (trajectory: arg-max + re-check | bucketing | E, PE |
+ * band solver; DTW: template transpose | fused kernel).  vcb_stage_times waits for the last mark of
+ * the most recent call and returns the stage durations in milliseconds (count <= capacity),
+ * averaged over the calls of that kind recorded since timing was enabled (the last 64 at most), so
+ * a loop may enqueue its steps back to back and read the times once at the end.
+ * Process-wide and not meant for concurrent callers. */
+int32_t vcb_stage_timing(int32_t enable);
+int32_t vcb_stage_times(double* ms, int32_t capacity, int32_t* count);
+
 /* ---------------------------------------------------------------------------------------------
  * GMMMap -- replaces GMMMap(weights, mu, Sigma; swap) (src/gmmmap.jl:62-90), GMMMapParam
  * (src/gmmmap.jl:10-39), split_joint_gmm (:41-52) and GaussianMixtureModel (src/gmm.jl:8-20).
@@ -113,6 +123,12 @@ int32_t vcb_gmmmap_predict(const vcb_gmmmap* g, const double* X, int32_t xrows, 
 /* Precomputes Dy_m = (Syy_m - A_m Sxy_m)^-1 (LU inverse).  dim(g) must be even (static+delta). */
 int32_t vcb_traj_create(const vcb_gmmmap* g, vcb_traj** out);
 int32_t vcb_traj_destroy(vcb_traj* t);
+/* The band solver is a Cholesky of W' D^-1 W (src/trajectory_gmmmap.jl:105, where the reference's
+ * sparse `\` falls back to LU).  If some Dy_m is not positive definite a pivot fails: the host entry
+ * points then return VCB_ENOTPD; after *_dev calls, vcb_traj_status(t, stream) synchronises the
+ * stream and returns VCB_ENOTPD if any conversion enqueued on this handle since the last query met
+ * such a pivot (the flag is cleared by the query), VCB_OK otherwise. */
+int32_t vcb_traj_status(const vcb_traj* t, void* stream);
 /* Dy (dim, dim, M) as the reference stores it (src/trajectory_gmmmap.jl:24-28). */
 int32_t vcb_traj_get_Dy(const vcb_traj* t, double* out);
 /* Batched fvconvert / vc.  X holds the frames of nseq utterances back to back: (xrows, total)

@@ -46,6 +46,32 @@ def test_ragged_and_tiny(vcb, oracle):
         assert np.array_equal(paths, ref) and np.array_equal(fc, rfc)
 
 
+@pytest.mark.parametrize("S,T", [(1025, 40), (1500, 300), (2500, 120), (4097, 33), (8192, 17)])
+def test_long_templates_bit_exact(vcb, oracle, S, T):
+    """Templates beyond 1024 frames (5.1 s at the reference's 5 ms shift): the reference has no
+    length limit (src/dtw.jl:93-98); several states per thread keep one CTA per pair."""
+    tm, to, sq, so = vcb.synth.dtw_pairs(2, 24, (S, S), 1300 + S)
+    so = np.array([0, T, 2 * T], dtype=np.int64)
+    sq = np.asfortranarray(np.concatenate([sq[:, :T], sq[:, S:S + T]], axis=1))
+    for fs, bs, D in [(0, 2, 24), (0, 1, 24), (1, 2, 24), (0, 2, 7)]:
+        a, b = np.asfortranarray(tm[:D]), np.asfortranarray(sq[:D])
+        paths, fc = vcb.DTWs.fit_batch(vcb.DTWs.DTW(fstep=fs, bstep=bs), a, to, b, so)
+        ref, rfc = oracle.dtw_fit_batch(a, to, b, so, fs, bs, nthreads=2)
+        assert np.array_equal(paths, ref) and np.array_equal(fc, rfc), (fs, bs, D)
+
+
+def test_mixed_long_and_short_batch(vcb, oracle):
+    tm, to, sq, so = vcb.synth.dtw_pairs(3, 24, (1200, 1700), 1400)
+    tm2, to2, sq2, so2 = vcb.synth.dtw_pairs(3, 24, (40, 90), 1401)
+    T = np.concatenate([tm, tm2], 1); Q = np.concatenate([sq, sq2], 1)
+    TO = np.concatenate([to, to[-1] + to2[1:]]); SO = np.concatenate([so, so[-1] + so2[1:]])
+    paths, fc = vcb.DTWs.fit_batch(vcb.DTWs.DTW(fstep=0, bstep=2), T, TO, Q, SO)
+    ref, rfc = oracle.dtw_fit_batch(T, TO, Q, SO, 0, 2, nthreads=oracle.max_threads())
+    assert np.array_equal(paths, ref) and np.array_equal(fc, rfc)
+    with pytest.raises(vcb.VCBError):                      # one CTA holds at most 8192 states
+        vcb.DTWs.fit(vcb.DTWs.DTW(), np.zeros((2, 8193)), np.zeros((2, 4)))
+
+
 def test_ties_follow_reference_order(vcb, oracle):
     # integer-valued features produce many exact ties: candidate order and strict '<' matter
     rng = np.random.default_rng(9)

@@ -57,6 +57,55 @@ def test_c2_shaped_batch(vcb, oracle, variant, limit):
     assert np.abs(out - ref).max() <= tol_for(ref[1:])
 
 
+@pytest.mark.parametrize("limit", [500, 100])
+def test_c4_shaped(vcb, oracle, variant, limit):
+    """BASELINE config 5 (C4) shape: 128 mixtures, static dimension 24, utterances of 500 frames;
+    chunk limits 500 (one solve per utterance) and 100 (the CLI default, bin/vc.jl:18).  The
+    arg-max mixture sequence must be exact, y within the 1e-4 bar (src/common.jl:31-63,
+    src/trajectory_gmmmap.jl:65-110)."""
+    gm, fm, off = vcb.synth.config_c2(16, 500, M=128, seed=1004)
+    g, o = vcb.GMMMap(*gm), oracle.GMMMap(*gm)
+    ref = oracle.vc_traj_batch(o, limit, fm, off, nthreads=oracle.max_threads())
+    t = vcb.TrajectoryGMMMap(g, limit)
+    out = np.concatenate(vcb.vc_batch(t, fm, off), axis=1)
+    assert out.shape == (25, 8000) and np.array_equal(out[0], fm[0])
+    assert np.abs(out - ref).max() <= tol_for(ref[1:])
+    # arg-max sequence of two whole utterances through fvconvert's side output
+    X = np.asfortranarray(fm[1:, :1000])
+    _, mh, _ = vcb.fvconvert(vcb.TrajectoryGMMMap(g, 1000), X, return_aux=True)
+    assert np.array_equal(mh, o.predict(X))
+    # the sharded indexed generator used by bench.py --path traj produces distinct utterances
+    fa, oa = vcb.synth.c4_utterances(gm, np.array([3, 5000]), 500)
+    fb, _ = vcb.synth.c4_utterances(gm, np.array([5000]), 500)
+    assert np.array_equal(fa[:, 500:], fb) and not np.array_equal(fa[:, :500], fb)
+
+
+def test_indefinite_precision_is_reported(vcb):
+    """A joint covariance whose yy block is indefinite gives an indefinite Dy: the reference's
+    sparse `\\` would still return something (LU); the band Cholesky reports PosDefException
+    instead of returning NaN (host path) and raises from vcb_traj_status after device calls."""
+    import torch
+    gm = vcb.synth.random_joint_gmm(77, 3, 16)                 # dim(g) = 8 = [static 4; delta 4]
+    cov = gm.covars.copy()
+    cov[8:, 8:, 1] -= 3.0 * np.eye(8) * np.abs(cov[8:, 8:, 1]).max()             # Syy indefinite, Sxx stays PD
+    g = vcb.GMMMap(gm.weights, gm.means, cov)
+    t = vcb.TrajectoryGMMMap(g, 50)
+    fm, off = vcb.synth.trajectory_utterances(gm, 2, 50, 78)
+    mh = vcb.predict(g, np.asfortranarray(fm[1:]))
+    assert (mh == 2).any()                                 # the broken mixture is actually used
+    with pytest.raises(vcb.PosDefException):
+        vcb.vc_batch(t, fm, off)
+    dfm = torch.from_numpy(np.ascontiguousarray(fm.T)).cuda()
+    vcb.vc_batch(t, dfm, off)                              # enqueues; no synchronisation, no error yet
+    with pytest.raises(vcb.PosDefException):
+        vcb.traj_status(t)
+    vcb.traj_status(t)                                     # the flag is cleared by the query
+    # a healthy model on the same handle type stays clean
+    t2 = vcb.TrajectoryGMMMap(vcb.GMMMap(*gm), 50)
+    vcb.vc_batch(t2, dfm, off)
+    vcb.traj_status(t2)
+
+
 def test_ragged_batch_and_state(vcb, oracle):
     gm = vcb.synth.random_joint_gmm(41, 5, 24)                        # Ds = 6
     fm, off = vcb.synth.trajectory_utterances(gm, 9, (1, 70), 42)

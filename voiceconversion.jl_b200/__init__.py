@@ -24,7 +24,8 @@ import numpy as np
 
 from . import _lib
 from ._lib import (ArgumentError, CudaError, DimensionMismatch, PosDefException, SingularException,  # noqa: F401
-                   VCBError, device_count, launch_count, set_device, set_kernel_variant)
+                   VCBError, device_count, launch_count, set_device, set_kernel_variant, stage_timing,
+                   stage_times)
 from . import dtws as DTWs  # noqa: N812  (Julia sub-module name, src/dtw.jl:1)
 from . import jld, shard, synth  # noqa: F401
 
@@ -34,7 +35,7 @@ __all__ = [
     "fvconvert", "fvconvert_gv", "vc", "vc_batch", "vc_static_batch", "ncomponents", "dim", "predict_proba",
     "predict", "constructW", "push_delta", "align", "align_batch", "DTWs", "DimensionMismatch",
     "PosDefException", "SingularException", "ArgumentError", "CudaError", "VCBError",
-    "set_device", "device_count", "set_kernel_variant", "launch_count",
+    "set_device", "device_count", "set_kernel_variant", "launch_count", "traj_status",
 ]
 
 
@@ -240,6 +241,29 @@ class VarianceScaling(NamedTuple):
     sigma2: np.ndarray
 
 
+def traj_status(t: "TrajectoryGMMMap") -> None:
+    """After device-resident (``*_dev``) conversions: synchronises the current stream and raises
+    ``PosDefException`` if any of them met a non-positive pivot of ``W' D^-1 W`` (an indefinite
+    ``Dy``) since the last query.  Host-array conversions raise by themselves."""
+    st = None
+    try:
+        import torch
+        if torch.cuda.is_available():
+            st = _stream_ptr()
+    except ImportError:
+        pass
+    _lib.check(_lib.lib().vcb_traj_status(t._h, st))
+
+
+def _check_offsets(off: np.ndarray, total: int) -> np.ndarray:
+    """offsets (n+1) must start at >= 0, be non-decreasing and stay inside the array."""
+    if off.ndim != 1 or len(off) < 1:
+        raise ArgumentError(_lib.EARG, "offsets must be a vector of n+1 frame offsets")
+    if len(off) > 1 and (off[0] < 0 or np.any(np.diff(off) < 0) or off[-1] > total):
+        raise ArgumentError(_lib.EARG, "offsets must be non-decreasing and within the %d frames of the array" % total)
+    return off
+
+
 def fvpostf(vs: VarianceScaling, src, offsets=None):
     """``fvpostf(vs, src)`` (src/gv.jl:17-21): per-dimension variance scaling of one (D, T) matrix,
     of a concatenated batch with ``offsets`` (one filter per utterance), or of a frame-major CUDA
@@ -250,7 +274,10 @@ def fvpostf(vs: VarianceScaling, src, offsets=None):
         import torch
         _check_dev_tensor(src)
         T, D = src.shape
+        if s2.shape != (D,):
+            raise DimensionMismatch(_lib.EDIM, "VarianceScaling has %d entries, src has %d rows" % (s2.size, D))
         off = np.array([0, T], dtype=np.int64) if offsets is None else np.ascontiguousarray(offsets, dtype=np.int64)
+        _check_offsets(off, T)
         out = torch.empty_like(src)
         d_s2 = torch.from_numpy(s2).to(src.device)
         _lib.check(L.vcb_variance_scaling_batch_dev(_lib.ptr(d_s2), D, _lib.ptr(src), D, _lib.ptr(off), len(off) - 1,
@@ -261,6 +288,7 @@ def fvpostf(vs: VarianceScaling, src, offsets=None):
     if s2.shape != (D,):
         raise DimensionMismatch(_lib.EDIM, "VarianceScaling has %d entries, src has %d rows" % (s2.size, D))
     off = np.array([0, T], dtype=np.int64) if offsets is None else np.ascontiguousarray(offsets, dtype=np.int64)
+    _check_offsets(off, T)
     out = np.empty_like(src, order="F")
     _lib.check(L.vcb_variance_scaling_batch(_lib.ptr(s2), D, _lib.ptr(src), D, _lib.ptr(off), len(off) - 1, _lib.ptr(out), D))
     return out
@@ -440,14 +468,16 @@ def vc(c, fm, out=None):
     raise TypeError("vc: unsupported converter type")
 
 
-def vc_batch(c, fms, offsets=None, _split: bool = True, epochs: int = 100, alpha: float = 1.0e-5):
+def vc_batch(c, fms, offsets=None, _split: bool = True, epochs: int = 100, alpha: float = 1.0e-5, out=None):
     """Batch extension of ``vc(c::TrajectoryConverter, fm)``: every utterance is converted as
     ``vc(c, fm_s)`` would with the chunk limit ``len(c)`` read once (src/common.jl:43), all in one
     library call.  ``fms`` is a list of (1+2Ds, T_s) matrices, or one concatenated matrix /
     frame-major CUDA tensor together with ``offsets`` (n+1, in frames).
 
     Like the reference, the converter remembers the length of the last chunk it solved
-    (src/trajectory_gmmmap.jl:70-72), so ``len(c)`` may change.
+    (src/trajectory_gmmmap.jl:70-72), so ``len(c)`` may change.  ``out`` (host path with
+    ``offsets``) is an optional preallocated column-major (1+Ds, total) result buffer, e.g.
+    page-locked memory.
     """
     L = _lib.lib()
     limit = len(c)
@@ -460,6 +490,7 @@ def vc_batch(c, fms, offsets=None, _split: bool = True, epochs: int = 100, alpha
         _check_dev_tensor(fms)
         off = np.ascontiguousarray(offsets, dtype=np.int64)
         total, rows = fms.shape
+        _check_offsets(off, total)
         out = torch.empty((total, Ds + 1), dtype=torch.float64, device=fms.device)
         if gv:
             _lib.check(L.vcb_trajgv_vc_batch_dev(cgv._h, _lib.ptr(fms), rows, _lib.ptr(off), len(off) - 1, limit,
@@ -480,8 +511,11 @@ def vc_batch(c, fms, offsets=None, _split: bool = True, epochs: int = 100, alpha
     else:
         fm = _f64(fms)
         rows = fm.shape[0]
-        off = np.ascontiguousarray(offsets, dtype=np.int64)
-    out = np.empty((Ds + 1, fm.shape[1]), order="F")
+        off = _check_offsets(np.ascontiguousarray(offsets, dtype=np.int64), fm.shape[1])
+    if out is None:
+        out = np.empty((Ds + 1, fm.shape[1]), order="F")
+    elif out.shape != (Ds + 1, fm.shape[1]) or out.dtype != np.float64 or not out.flags.f_contiguous:
+        raise ArgumentError(_lib.EARG, "out must be a column-major float64 array of shape (1 + dim/2, total frames)")
     if gv:
         _lib.check(L.vcb_trajgv_vc_batch(cgv._h, _lib.ptr(fm), rows, _lib.ptr(off), len(off) - 1, limit, int(epochs),
                                          float(alpha), _lib.ptr(out)))
@@ -505,11 +539,13 @@ def vc_static_batch(c: TrajectoryGMMMap, fm, offsets):
         import torch
         _check_dev_tensor(fm)
         total, rows = fm.shape
+        _check_offsets(off, total)
         out = torch.empty((total, Ds + 1), dtype=torch.float64, device=fm.device)
         _lib.check(L.vcb_traj_vc_static_batch_dev(c._h, _lib.ptr(fm), rows, _lib.ptr(off), len(off) - 1, limit,
                                                   _lib.ptr(out), _stream_ptr()))
     else:
         fm = _f64(fm)
+        _check_offsets(off, fm.shape[1])
         out = np.empty((Ds + 1, fm.shape[1]), order="F")
         _lib.check(L.vcb_traj_vc_static_batch(c._h, _lib.ptr(fm), fm.shape[0], _lib.ptr(off), len(off) - 1, limit,
                                               _lib.ptr(out)))
@@ -550,6 +586,7 @@ def push_delta(src, offsets=None) -> np.ndarray:
     """``push_delta(src)`` (src/datasets.jl:6-13); with ``offsets`` a ragged batch in one call."""
     s = _f64(src)
     off = np.array([0, s.shape[1]], dtype=np.int64) if offsets is None else np.ascontiguousarray(offsets, dtype=np.int64)
+    _check_offsets(off, s.shape[1])
     out = np.empty((2 * s.shape[0], s.shape[1]), order="F")
     _lib.check(_lib.lib().vcb_push_delta_batch(_lib.ptr(s), s.shape[0], _lib.ptr(off), len(off) - 1, _lib.ptr(out)))
     return out
@@ -560,8 +597,10 @@ def align_batch(src, src_off, tgt, tgt_off):
     s, t = _f64(src), _f64(tgt)
     if s.shape[0] != t.shape[0]:
         raise DimensionMismatch(_lib.EDIM, "order of feature vector must be equal")
-    so = np.ascontiguousarray(src_off, dtype=np.int64)
-    to = np.ascontiguousarray(tgt_off, dtype=np.int64)
+    so = _check_offsets(np.ascontiguousarray(src_off, dtype=np.int64), s.shape[1])
+    to = _check_offsets(np.ascontiguousarray(tgt_off, dtype=np.int64), t.shape[1])
+    if len(so) != len(to):
+        raise ArgumentError(_lib.EARG, "src_off and tgt_off must describe the same number of pairs")
     newtgt = np.empty_like(s, order="F")
     paths = np.empty(t.shape[1], dtype=np.int64)
     _lib.check(_lib.lib().vcb_align_batch(_lib.ptr(s), _lib.ptr(so), _lib.ptr(t), _lib.ptr(to), len(so) - 1, s.shape[0],

@@ -66,6 +66,8 @@ SIGNATURES = {
     "vcb_host_unregister": (_i32, [_vp]),
     "vcb_set_kernel_variant": (_i32, [_i32]),
     "vcb_launch_count": (_i64, []),
+    "vcb_stage_timing": (_i32, [_i32]),
+    "vcb_stage_times": (_i32, [_vp, _i32, C.POINTER(_i32)]),
     "vcb_gmmmap_create": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, C.POINTER(_vp)]),
     "vcb_gmmmap_destroy": (_i32, [_vp]),
     "vcb_gmmmap_dim": (_i32, [_vp, C.POINTER(_i32)]),
@@ -79,6 +81,7 @@ SIGNATURES = {
     "vcb_gmmmap_predict": (_i32, [_vp, _vp, _i32, _i64, _i64, _vp]),
     "vcb_traj_create": (_i32, [_vp, C.POINTER(_vp)]),
     "vcb_traj_destroy": (_i32, [_vp]),
+    "vcb_traj_status": (_i32, [_vp, _vp]),
     "vcb_traj_get_Dy": (_i32, [_vp, _vp]),
     "vcb_traj_convert_batch": (_i32, [_vp, _vp, _i32, _i64, _vp, _i64, _i32, _vp, _i64, _vp, _vp]),
     "vcb_traj_convert_batch_dev": (_i32, [_vp, _vp, _i32, _i64, _vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp]),
@@ -159,3 +162,16 @@ def set_kernel_variant(variant: int) -> None:
 
 def launch_count() -> int:
     return int(lib().vcb_launch_count())
+
+
+def stage_timing(enable: bool) -> None:
+    """Profiling aid: record CUDA events between the stages of trajectory / DTW device calls."""
+    check(lib().vcb_stage_timing(int(bool(enable))))
+
+
+def stage_times():
+    """Stage durations (ms) of the most recent trajectory / DTW device call (synchronises on it)."""
+    buf = (C.c_double * 12)()
+    n = _i32(0)
+    check(lib().vcb_stage_times(buf, 12, C.byref(n)))
+    return [buf[i] for i in range(n.value)]

@@ -14,6 +14,42 @@ static thread_local std::string t_last_error;
 std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_variant{0};
 
+namespace {
+// Ring of per-call event sets: the marks of up to kCalls consecutive calls stay readable, so a
+// benchmark loop can enqueue its steps back to back and read the stage times afterwards.
+struct StageTimer {
+    std::atomic<bool> on{false};
+    static constexpr int kMax = 8, kCalls = 64;
+    cudaEvent_t ev[kCalls][kMax] = {};
+    int n[kCalls] = {};
+    int64_t calls = 0;      // calls recorded since timing was enabled
+    int device = -1;
+} g_stages;
+}  // namespace
+
+void stage_begin(cudaStream_t st) {
+    if (!g_stages.on.load(std::memory_order_relaxed)) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (g_stages.device != dev) {      // events belong to a device: (re)create them here
+        for (auto& set : g_stages.ev)
+            for (auto& e : set) {
+                if (e) cudaEventDestroy(e);
+                cudaEventCreate(&e);
+            }
+        g_stages.device = dev;
+    }
+    const int slot = (int)(g_stages.calls++ % StageTimer::kCalls);
+    g_stages.n[slot] = 0;
+    stage_mark(st);
+}
+void stage_mark(cudaStream_t st) {
+    if (!g_stages.on.load(std::memory_order_relaxed) || g_stages.calls == 0 || g_stages.device < 0) return;
+    const int slot = (int)((g_stages.calls - 1) % StageTimer::kCalls);
+    if (g_stages.n[slot] >= StageTimer::kMax) return;
+    cudaEventRecord(g_stages.ev[slot][g_stages.n[slot]++], st);
+}
+
 int32_t fail(int32_t code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
@@ -49,10 +85,38 @@ static int32_t ensure_device(int* dev_out = nullptr) {
     return VCB_OK;
 }
 
-static int32_t use_device_of(int handle_dev) {
-    int dev = -1;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev != handle_dev) VCB_CUDA(cudaSetDevice(handle_dev));
+// Makes the handle's device current for the duration of one library call and puts the caller's
+// device back on return (a destroy running inside a garbage collector must not move torch's or
+// Julia's current device).
+struct DeviceGuard {
+    int prev = -1;
+    bool moved = false;
+    int32_t enter(int handle_dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != handle_dev) {
+            VCB_CUDA(cudaSetDevice(handle_dev));
+            moved = true;
+        }
+        return VCB_OK;
+    }
+    ~DeviceGuard() {
+        if (moved && prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define VCB_ON_DEVICE(dev) DeviceGuard _dg; VCB_TRY(_dg.enter(dev))
+
+// Reads and clears the trajectory handle's pivot flag (stream already synchronised or ordered).
+static int32_t traj_take_status(const vcb_traj& t, cudaStream_t st, bool* not_pd) {
+    int h = 0;
+    VCB_CUDA(cudaMemcpyAsync(&h, t.d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    VCB_CUDA(cudaStreamSynchronize(st));
+    if (h) VCB_CUDA(cudaMemsetAsync(t.d_err.p, 0, sizeof(int), st));
+    *not_pd = h != 0;
     return VCB_OK;
+}
+static int32_t traj_not_pd() {
+    return fail(VCB_ENOTPD, "W' D^-1 W is not positive definite: some Dy[:,:,m] = (Syy - A Sxy)^-1 is indefinite "
+                            "(src/trajectory_gmmmap.jl:24-28, :105); the band Cholesky cannot solve it");
 }
 
 // Scratch that lives for one host call.
@@ -137,7 +201,9 @@ static int32_t traj_device(const vcb_traj& t, const double* dX, int64_t ldx, con
     VCB_CUDA(sc.get(&d_chunks, chunks.size()));
     VCB_CUDA(cudaMemcpyAsync(d_chunks, chunks.data(), chunks.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     const double* X0 = dX + base * ldx;
+    stage_begin(st);
     VCB_TRY(argmax_device(g, X0, total, ldx, d_mhat, st));                       // src/trajectory_gmmmap.jl:82
+    stage_mark(st);      // [0] arg-max (+ Float64 re-check)
     // bucket the frames by arg-max mixture once; E_t / P_t E_t and the GV gradient run as per-mixture GEMMs
     static const bool per_frame = [] { const char* e = getenv("VCB_TRAJ_E"); return e && e[0] == 'f'; }();
     int* ws = nullptr;
@@ -146,6 +212,7 @@ static int32_t traj_device(const vcb_traj& t, const double* dX, int64_t ldx, con
         VCB_CUDA(sc.get(&ws, group_workspace_ints(g.M, total)));
         VCB_TRY(group_frames_by_mixture(d_mhat, total, g.M, ws, &npanels, st));
     }
+    stage_mark(st);      // [1] bucketing by mixture; traj_solve_device marks [2] E / PE and [3] the band solver
     VCB_TRY(traj_solve_device(t, X0, ldx, d_mhat, d_chunks, nchunks, maxlen, total, dY + base * ldy, ldy,
                               dEy ? dEy + base * g.D : nullptr, copy_power, st, ws, npanels));
     if (dmhat) VCB_TRY(widen_mhat(d_mhat, total, dmhat + base, st));
@@ -206,6 +273,38 @@ int32_t vcb_set_kernel_variant(int32_t variant) {
 }
 int64_t vcb_launch_count(void) { return g_launches.load(); }
 
+int32_t vcb_stage_timing(int32_t enable) {
+    g_stages.on.store(enable != 0);
+    g_stages.calls = 0;
+    return VCB_OK;
+}
+int32_t vcb_stage_times(double* ms, int32_t capacity, int32_t* count) {
+    if (!ms || !count || capacity < 0) return fail(VCB_EARG, "null argument");
+    *count = 0;
+    const int64_t ncalls = std::min<int64_t>(g_stages.calls, StageTimer::kCalls);
+    if (ncalls == 0) return VCB_OK;
+    const int last = (int)((g_stages.calls - 1) % StageTimer::kCalls);
+    const int marks = g_stages.n[last];
+    if (marks < 2) return VCB_OK;
+    VCB_CUDA(cudaEventSynchronize(g_stages.ev[last][marks - 1]));
+    const int nst = std::min(marks - 1, (int)capacity);
+    for (int i = 0; i < nst; ++i) ms[i] = 0.0;
+    int used = 0;
+    for (int64_t c = 0; c < ncalls; ++c) {
+        const int slot = (int)((g_stages.calls - 1 - c) % StageTimer::kCalls);
+        if (g_stages.n[slot] != marks) continue;     // a call of another kind (e.g. DTW between trajectories)
+        for (int i = 0; i < nst; ++i) {
+            float f = 0.f;
+            VCB_CUDA(cudaEventElapsedTime(&f, g_stages.ev[slot][i], g_stages.ev[slot][i + 1]));
+            ms[i] += f;
+        }
+        ++used;
+    }
+    for (int i = 0; i < nst; ++i) ms[i] /= used;
+    *count = nst;
+    return VCB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // GMMMap
 // ------------------------------------------------------------------------------------------------
@@ -227,7 +326,8 @@ int32_t vcb_gmmmap_create(const double* weights, const double* mu, const double*
 
 int32_t vcb_gmmmap_destroy(vcb_gmmmap* g) {
     if (!g) return VCB_OK;
-    use_device_of(g->device);
+    DeviceGuard dg;
+    dg.enter(g->device);
     delete g;
     return VCB_OK;
 }
@@ -272,7 +372,7 @@ int32_t vcb_gmmmap_convert_dev(const vcb_gmmmap* g, const double* dX, int32_t xr
     if (!g || (T > 0 && (!dX || !dY))) return fail(VCB_EARG, "null argument");
     if (xrows != g->D) return fail(VCB_EDIM, "Inconsistent dimentions. (frame has %d rows, dim(g) = %d)", xrows, g->D);
     if (T < 0 || ldx < xrows || ldy < xrows) return fail(VCB_EARG, "bad T/ld (T=%lld ldx=%lld ldy=%lld)", (long long)T, (long long)ldx, (long long)ldy);
-    VCB_TRY(use_device_of(g->device));
+    VCB_ON_DEVICE(g->device);
     return convert_device(*g, dX, T, ldx, dY, ldy, false, (cudaStream_t)stream);
     VCB_GUARD_END
 }
@@ -283,7 +383,7 @@ int32_t vcb_gmmmap_vc_dev(const vcb_gmmmap* g, const double* dfm, int32_t rows, 
     if (!g || (T > 0 && (!dfm || !dout))) return fail(VCB_EARG, "null argument");
     if (rows != g->D + 1) return fail(VCB_EDIM, "Inconsistent dimentions. (feature matrix has %d rows, expected 1 + dim(g) = %d)", rows, g->D + 1);
     if (T < 0) return fail(VCB_EARG, "negative T");
-    VCB_TRY(use_device_of(g->device));
+    VCB_ON_DEVICE(g->device);
     return convert_device(*g, dfm + 1, T, rows, dout + 1, rows, true, (cudaStream_t)stream);
     VCB_GUARD_END
 }
@@ -403,7 +503,7 @@ int32_t vcb_gmmmap_convert(const vcb_gmmmap* g, const double* X, int32_t xrows, 
     if (!g || (T > 0 && (!X || !Y))) return fail(VCB_EARG, "null argument");
     if (xrows != g->D) return fail(VCB_EDIM, "Inconsistent dimentions. (frame has %d rows, dim(g) = %d)", xrows, g->D);
     if (T < 0 || ldx < xrows || ldy < xrows) return fail(VCB_EARG, "bad T/ld");
-    VCB_TRY(use_device_of(g->device));
+    VCB_ON_DEVICE(g->device);
     return fbf_host(*g, X, T, ldx, Y, ldy, false);
     VCB_GUARD_END
 }
@@ -413,7 +513,7 @@ int32_t vcb_gmmmap_vc(const vcb_gmmmap* g, const double* fm, int32_t rows, int64
     if (!g || (T > 0 && (!fm || !out))) return fail(VCB_EARG, "null argument");
     if (rows != g->D + 1) return fail(VCB_EDIM, "Inconsistent dimentions. (feature matrix has %d rows, expected 1 + dim(g) = %d)", rows, g->D + 1);
     if (T < 0) return fail(VCB_EARG, "negative T");
-    VCB_TRY(use_device_of(g->device));
+    VCB_ON_DEVICE(g->device);
     return fbf_host(*g, fm + 1, T, rows, out + 1, rows, true);
     VCB_GUARD_END
 }
@@ -425,7 +525,7 @@ int32_t vcb_gmmmap_predict_proba(const vcb_gmmmap* g, const double* X, int32_t x
     if (xrows != g->D) return fail(VCB_EDIM, "Inconsistent dimentions. (frame has %d rows, dim(g) = %d)", xrows, g->D);
     if (T < 0 || ldx < xrows) return fail(VCB_EARG, "bad T/ld");
     if (T == 0) return VCB_OK;
-    VCB_TRY(use_device_of(g->device));
+    VCB_ON_DEVICE(g->device);
     cudaStream_t st = nullptr;
     Scratch sc(st);
     double *dX = nullptr, *dP = nullptr;
@@ -447,7 +547,7 @@ int32_t vcb_gmmmap_predict(const vcb_gmmmap* g, const double* X, int32_t xrows, 
     if (xrows != g->D) return fail(VCB_EDIM, "Inconsistent dimentions. (frame has %d rows, dim(g) = %d)", xrows, g->D);
     if (T < 0 || ldx < xrows) return fail(VCB_EARG, "bad T/ld");
     if (T == 0) return VCB_OK;
-    VCB_TRY(use_device_of(g->device));
+    VCB_ON_DEVICE(g->device);
     cudaStream_t st = nullptr;
     Scratch sc(st);
     double* dX = nullptr;
@@ -473,7 +573,7 @@ int32_t vcb_traj_create(const vcb_gmmmap* g, vcb_traj** out) {
     VCB_GUARD_BEGIN
     if (!g || !out) return fail(VCB_EARG, "null argument");
     *out = nullptr;
-    VCB_TRY(use_device_of(g->device));
+    VCB_ON_DEVICE(g->device);
     vcb_traj* t = new vcb_traj();
     int32_t rc = build_traj(*g, *t);
     if (rc != VCB_OK) { delete t; return rc; }
@@ -484,9 +584,20 @@ int32_t vcb_traj_create(const vcb_gmmmap* g, vcb_traj** out) {
 
 int32_t vcb_traj_destroy(vcb_traj* t) {
     if (!t) return VCB_OK;
-    use_device_of(t->g->device);
+    DeviceGuard dg;
+    dg.enter(t->device);     // not t->g->device: the parent may already be gone
     delete t;
     return VCB_OK;
+}
+
+int32_t vcb_traj_status(const vcb_traj* t, void* stream) {
+    VCB_GUARD_BEGIN
+    if (!t) return fail(VCB_EARG, "null argument");
+    VCB_ON_DEVICE(t->device);
+    bool not_pd = false;
+    VCB_TRY(traj_take_status(*t, (cudaStream_t)stream, &not_pd));
+    return not_pd ? traj_not_pd() : VCB_OK;
+    VCB_GUARD_END
 }
 
 int32_t vcb_traj_get_Dy(const vcb_traj* t, double* out) {
@@ -511,7 +622,7 @@ int32_t vcb_traj_convert_batch_dev(const vcb_traj* t, const double* dX, int32_t 
     VCB_TRY(traj_check(t, xrows, ldx, offsets, nseq));
     if (!dX || !dY) return fail(VCB_EARG, "null argument");
     if (ldy < t->Ds) return fail(VCB_EARG, "ldy < dim/2");
-    VCB_TRY(use_device_of(t->g->device));
+    VCB_ON_DEVICE(t->device);
     return traj_device(*t, dX, ldx, offsets, nseq, chunk_limit, dY, ldy, dmhat, dEy, false, (cudaStream_t)stream);
     VCB_GUARD_END
 }
@@ -521,21 +632,21 @@ int32_t vcb_traj_vc_batch_dev(const vcb_traj* t, const double* dfm, int32_t rows
     VCB_GUARD_BEGIN
     VCB_TRY(traj_check(t, rows - 1, rows, offsets, nseq));
     if (!dfm || !dout) return fail(VCB_EARG, "null argument");
-    VCB_TRY(use_device_of(t->g->device));
+    VCB_ON_DEVICE(t->device);
     return traj_device(*t, dfm + 1, rows, offsets, nseq, chunk_limit, dout + 1, t->Ds + 1, nullptr, nullptr, true,
                        (cudaStream_t)stream);
     VCB_GUARD_END
 }
 
-static int32_t traj_host(const vcb_traj& t, const double* X, int64_t ldx, const int64_t* offsets, int64_t nseq,
-                         int chunk_limit, double* Y, int64_t ldy, int64_t* mhat, double* Ey, bool whole_rows,
-                         GvRun gvr = GvRun()) {
-    if (nseq == 0) return VCB_OK;
-    const int64_t base = offsets[0], total = offsets[nseq] - base;
+// One slice of utterances [s0, s1) of a host batch on one stream: H2D, conversion, D2H; no
+// synchronisation (the per-call scratch is released in stream order).
+static int32_t traj_host_slice(const vcb_traj& t, const double* X, int64_t ldx, const int64_t* offsets, int64_t s0,
+                               int64_t s1, int chunk_limit, double* Y, int64_t ldy, int64_t* mhat, double* Ey,
+                               bool whole_rows, GvRun gvr, cudaStream_t st) {
+    const int64_t base = offsets[s0], total = offsets[s1] - base;
     if (total <= 0) return VCB_OK;
     const int D2 = t.g->D, Ds = t.Ds;
     const int64_t pre = whole_rows ? 1 : 0;
-    cudaStream_t st = nullptr;
     Scratch sc(st);
     double *dX = nullptr, *dY = nullptr, *dE = nullptr;
     int64_t* dm = nullptr;
@@ -546,9 +657,9 @@ static int32_t traj_host(const vcb_traj& t, const double* X, int64_t ldx, const 
     if (mhat) VCB_CUDA(sc.get(&dm, (size_t)total));
     if (Ey) VCB_CUDA(sc.get(&dE, (size_t)total * D2));
     VCB_CUDA(cudaMemcpyAsync(dX, X + base * ldx - pre, in_elems * sizeof(double), cudaMemcpyHostToDevice, st));
-    std::vector<int64_t> rel(offsets, offsets + nseq + 1);
+    std::vector<int64_t> rel(offsets + s0, offsets + s1 + 1);
     for (auto& o : rel) o -= base;
-    VCB_TRY(traj_device(t, dX + pre, ldx, rel.data(), nseq, chunk_limit, dY + pre, ldy, dm, dE, whole_rows, st, gvr));
+    VCB_TRY(traj_device(t, dX + pre, ldx, rel.data(), s1 - s0, chunk_limit, dY + pre, ldy, dm, dE, whole_rows, st, gvr));
     if (whole_rows || ldy == Ds) {
         VCB_CUDA(cudaMemcpyAsync(Y + base * ldy - pre, dY, out_elems * sizeof(double), cudaMemcpyDeviceToHost, st));
     } else {
@@ -557,8 +668,51 @@ static int32_t traj_host(const vcb_traj& t, const double* X, int64_t ldx, const 
     }
     if (mhat) VCB_CUDA(cudaMemcpyAsync(mhat + base, dm, (size_t)total * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     if (Ey) VCB_CUDA(cudaMemcpyAsync(Ey + base * D2, dE, (size_t)total * D2 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    VCB_CUDA(cudaStreamSynchronize(st));
     return VCB_OK;
+}
+
+// Host batch: the utterances are cut into slices of about one solver wave (one warp per chunk, ~7
+// chunks per SM) that rotate through the cached streams, so the H2D copy of slice i+1 and the D2H
+// copy of slice i-1 run under the kernels of slice i.  The band solver is latency-bound (its time
+// hardly depends on the number of chunks up to a full wave), so smaller slices would not pay.
+static int32_t traj_host(const vcb_traj& t, const double* X, int64_t ldx, const int64_t* offsets, int64_t nseq,
+                         int chunk_limit, double* Y, int64_t ldy, int64_t* mhat, double* Ey, bool whole_rows,
+                         GvRun gvr = GvRun()) {
+    if (nseq == 0) return VCB_OK;
+    if (offsets[0] < 0) return fail(VCB_EARG, "offsets must start at a non-negative frame");
+    for (int64_t s = 0; s < nseq; ++s)
+        if (offsets[s + 1] < offsets[s]) return fail(VCB_EARG, "offsets must be non-decreasing");
+    if (offsets[nseq] - offsets[0] <= 0) return VCB_OK;
+    static const int64_t wave = [] { const char* e = getenv("VCB_TRAJ_SLICE_CHUNKS"); return e ? atoll(e) : 1036LL; }();
+    HostPipe* hp = pipe_acquire(t.device, 0, 0);
+    if (!hp) return fail(VCB_ECUDA, "stream creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    int32_t rc = VCB_OK;
+    int idx = 0;
+    for (int64_t s0 = 0; s0 < nseq && rc == VCB_OK; idx = (idx + 1) % kSlots) {
+        int64_t s1 = s0, chunks = 0;
+        while (s1 < nseq && (chunks < wave || s1 == s0)) {
+            const int64_t len = offsets[s1 + 1] - offsets[s1];
+            chunks += chunk_limit > 0 ? (len + chunk_limit - 1) / chunk_limit : (len > 0);
+            ++s1;
+        }
+        // do not leave a tail of less than half a wave for a slice of its own
+        int64_t rest = 0;
+        for (int64_t s = s1; s < nseq && rest < wave; ++s) {
+            const int64_t len = offsets[s + 1] - offsets[s];
+            rest += chunk_limit > 0 ? (len + chunk_limit - 1) / chunk_limit : (len > 0);
+        }
+        if (2 * rest < wave) s1 = nseq;
+        rc = traj_host_slice(t, X, ldx, offsets, s0, s1, chunk_limit, Y, ldy, mhat, Ey, whole_rows, gvr, hp->st[idx]);
+        s0 = s1;
+    }
+    for (int s = 0; s < kSlots; ++s)
+        if (cudaStreamSynchronize(hp->st[s]) != cudaSuccess && rc == VCB_OK)
+            rc = fail(VCB_ECUDA, "trajectory conversion failed: %s", cudaGetErrorString(cudaGetLastError()));
+    bool not_pd = false;
+    if (rc == VCB_OK) rc = traj_take_status(t, hp->st[0], &not_pd);
+    pipe_release(hp);
+    if (rc == VCB_OK && not_pd) rc = traj_not_pd();
+    return rc;
 }
 
 int32_t vcb_traj_convert_batch(const vcb_traj* t, const double* X, int32_t xrows, int64_t ldx,
@@ -568,7 +722,7 @@ int32_t vcb_traj_convert_batch(const vcb_traj* t, const double* X, int32_t xrows
     VCB_TRY(traj_check(t, xrows, ldx, offsets, nseq));
     if (!X || !Y) return fail(VCB_EARG, "null argument");
     if (ldy < t->Ds) return fail(VCB_EARG, "ldy < dim/2");
-    VCB_TRY(use_device_of(t->g->device));
+    VCB_ON_DEVICE(t->device);
     return traj_host(*t, X, ldx, offsets, nseq, chunk_limit, Y, ldy, mhat, Ey, false);
     VCB_GUARD_END
 }
@@ -578,7 +732,7 @@ int32_t vcb_traj_vc_batch(const vcb_traj* t, const double* fm, int32_t rows, con
     VCB_GUARD_BEGIN
     VCB_TRY(traj_check(t, rows - 1, rows, offsets, nseq));
     if (!fm || !out) return fail(VCB_EARG, "null argument");
-    VCB_TRY(use_device_of(t->g->device));
+    VCB_ON_DEVICE(t->device);
     return traj_host(*t, fm + 1, rows, offsets, nseq, chunk_limit, out + 1, t->Ds + 1, nullptr, nullptr, true);
     VCB_GUARD_END
 }
@@ -613,7 +767,7 @@ int32_t vcb_traj_vc_static_batch_dev(const vcb_traj* t, const double* dfm, int32
     if (!t || !offsets || !dfm || !dout) return fail(VCB_EARG, "null argument");
     if (nseq < 0) return fail(VCB_EARG, "negative nseq");
     if (rows != t->Ds + 1) return fail(VCB_EDIM, "Inconsistent dimentions. (static frame has %d rows, 1 + dim(t)/2 = %d)", rows, t->Ds + 1);
-    VCB_TRY(use_device_of(t->g->device));
+    VCB_ON_DEVICE(t->device);
     return traj_static_device(*t, dfm, offsets, nseq, chunk_limit, dout, (cudaStream_t)stream);
     VCB_GUARD_END
 }
@@ -625,7 +779,7 @@ int32_t vcb_traj_vc_static_batch(const vcb_traj* t, const double* fm, int32_t ro
     if (nseq < 0) return fail(VCB_EARG, "negative nseq");
     if (rows != t->Ds + 1) return fail(VCB_EDIM, "Inconsistent dimentions. (static frame has %d rows, 1 + dim(t)/2 = %d)", rows, t->Ds + 1);
     if (nseq == 0) return VCB_OK;
-    VCB_TRY(use_device_of(t->g->device));
+    VCB_ON_DEVICE(t->device);
     const int64_t base = offsets[0], total = offsets[nseq] - base;
     if (total <= 0) return VCB_OK;
     cudaStream_t st = nullptr;
@@ -639,8 +793,9 @@ int32_t vcb_traj_vc_static_batch(const vcb_traj* t, const double* fm, int32_t ro
     for (auto& o : rel) o -= base;
     VCB_TRY(traj_static_device(*t, dI, rel.data(), nseq, chunk_limit, dO, st));
     VCB_CUDA(cudaMemcpyAsync(out + base * rows, dO, n * sizeof(double), cudaMemcpyDeviceToHost, st));
-    VCB_CUDA(cudaStreamSynchronize(st));
-    return VCB_OK;
+    bool not_pd = false;
+    VCB_TRY(traj_take_status(*t, st, &not_pd));
+    return not_pd ? traj_not_pd() : VCB_OK;
     VCB_GUARD_END
 }
 
@@ -656,9 +811,10 @@ int32_t vcb_trajgv_create(const vcb_traj* t, const double* mu_v, const double* s
         if (mu_v[i] < 0.0) return fail(VCB_EARG, "GV mean %d is negative", i + 1);
     std::vector<double> pv(sigma_vv, sigma_vv + (size_t)Ds * Ds);
     if (!invert_matrix(pv, Ds)) return fail(VCB_ESINGULAR, "GV covariance is singular");   // inv(S_vv)  :125
-    VCB_TRY(use_device_of(t->g->device));
+    VCB_ON_DEVICE(t->device);
     vcb_trajgv* v = new vcb_trajgv();
     v->t = t;
+    v->device = t->device;
     v->muv.assign(mu_v, mu_v + Ds);
     v->pv = pv;
     if (v->d_muv.upload(v->muv) != cudaSuccess || v->d_pv.upload(v->pv) != cudaSuccess) {
@@ -672,7 +828,8 @@ int32_t vcb_trajgv_create(const vcb_traj* t, const double* mu_v, const double* s
 
 int32_t vcb_trajgv_destroy(vcb_trajgv* v) {
     if (!v) return VCB_OK;
-    use_device_of(v->t->g->device);
+    DeviceGuard dg;
+    dg.enter(v->device);
     delete v;
     return VCB_OK;
 }
@@ -691,7 +848,7 @@ int32_t vcb_trajgv_convert_batch_dev(const vcb_trajgv* v, const double* dX, int3
     VCB_TRY(traj_check(v->t, xrows, ldx, offsets, nseq));
     if (!dX || !dY) return fail(VCB_EARG, "null argument");
     if (ldy < v->t->Ds) return fail(VCB_EARG, "ldy < dim/2");
-    VCB_TRY(use_device_of(v->t->g->device));
+    VCB_ON_DEVICE(v->device);
     return traj_device(*v->t, dX, ldx, offsets, nseq, chunk_limit, dY, ldy, nullptr, nullptr, false,
                        (cudaStream_t)stream, GvRun{v, epochs, alpha});
     VCB_GUARD_END
@@ -704,7 +861,7 @@ int32_t vcb_trajgv_vc_batch_dev(const vcb_trajgv* v, const double* dfm, int32_t 
     VCB_TRY(gv_args(v, epochs));
     VCB_TRY(traj_check(v->t, rows - 1, rows, offsets, nseq));
     if (!dfm || !dout) return fail(VCB_EARG, "null argument");
-    VCB_TRY(use_device_of(v->t->g->device));
+    VCB_ON_DEVICE(v->device);
     return traj_device(*v->t, dfm + 1, rows, offsets, nseq, chunk_limit, dout + 1, v->t->Ds + 1, nullptr, nullptr, true,
                        (cudaStream_t)stream, GvRun{v, epochs, alpha});
     VCB_GUARD_END
@@ -718,7 +875,7 @@ int32_t vcb_trajgv_convert_batch(const vcb_trajgv* v, const double* X, int32_t x
     VCB_TRY(traj_check(v->t, xrows, ldx, offsets, nseq));
     if (!X || !Y) return fail(VCB_EARG, "null argument");
     if (ldy < v->t->Ds) return fail(VCB_EARG, "ldy < dim/2");
-    VCB_TRY(use_device_of(v->t->g->device));
+    VCB_ON_DEVICE(v->device);
     return traj_host(*v->t, X, ldx, offsets, nseq, chunk_limit, Y, ldy, nullptr, nullptr, false, GvRun{v, epochs, alpha});
     VCB_GUARD_END
 }
@@ -729,7 +886,7 @@ int32_t vcb_trajgv_vc_batch(const vcb_trajgv* v, const double* fm, int32_t rows,
     VCB_TRY(gv_args(v, epochs));
     VCB_TRY(traj_check(v->t, rows - 1, rows, offsets, nseq));
     if (!fm || !out) return fail(VCB_EARG, "null argument");
-    VCB_TRY(use_device_of(v->t->g->device));
+    VCB_ON_DEVICE(v->device);
     return traj_host(*v->t, fm + 1, rows, offsets, nseq, chunk_limit, out + 1, v->t->Ds + 1, nullptr, nullptr, true,
                      GvRun{v, epochs, alpha});
     VCB_GUARD_END

@@ -35,6 +35,12 @@ extern std::atomic<int> g_variant;  // 0 auto, 1 simt, 2 tcgen05
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+// Optional per-stage CUDA-event marks of the last trajectory / DTW device call (vcb_stage_timing):
+// bench.py uses them to time the dominant kernel alone inside its timed region.  Process-wide,
+// profiling only (not meant for concurrent callers).
+void stage_begin(cudaStream_t st);
+void stage_mark(cudaStream_t st);
+
 // Device buffer with RAII (handles and per-call scratch).
 template <class T>
 struct DevBuf {
@@ -109,14 +115,20 @@ struct vcb_gmmmap {
 
 struct vcb_traj;
 struct vcb_trajgv {
+    int device = 0;                   // own copy: the parent may be finalised first (unordered GC finalisers)
     const vcb_traj* t = nullptr;      // borrowed
     std::vector<double> muv, pv;      // GV mean (Ds), inv(S_vv) (Ds,Ds) column-major
     vcb::DevBuf<double> d_muv, d_pv;
 };
 
 struct vcb_traj {
+    int device = 0;             // own copy of g->device (see vcb_trajgv)
     const vcb_gmmmap* g = nullptr;
     int Ds = 0;                 // static dimension = dim(g)/2
     std::vector<double> Dy;     // (2Ds,2Ds,M) as the reference computes it (LU inverse)
     vcb::DevBuf<double> d_P;    // [M][2Ds*2Ds] symmetrised precision, column-major
+    // sticky device flag: a solver met a non-positive pivot of W' D^-1 W (some Dy_m is not positive
+    // definite).  Host entry points read and clear it after their synchronisation; *_dev callers
+    // query it with vcb_traj_status.
+    vcb::DevBuf<int> d_err;
 };

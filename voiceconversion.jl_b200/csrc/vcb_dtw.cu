@@ -25,6 +25,9 @@
 
 namespace vcb {
 
+// 1024 threads x 8 states; 41 s of speech at the reference's 5 ms frame shift
+constexpr int kDtwMaxStates = 8192;
+
 // tmpl (D, S) column-major per pair  ->  tmplT[k * S + i]
 __global__ void dtw_transpose_kernel(const double* __restrict__ tmpl, const int64_t* __restrict__ toff,
                                      double* __restrict__ tmplT, int D) {
@@ -50,8 +53,11 @@ __global__ void dtw_transpose_kernel(const double* __restrict__ tmpl, const int6
 }
 
 // DT > 0: feature dimension known at compile time (observation loop fully unrolled);
-// BS >= 0: window (bstep = BS, fstep = FS) known at compile time (candidate scan unrolled).
-template <int BITS, int TT, int MAXT, int MINB, int DT, int BS, int FS>
+// BS >= 0: window (bstep = BS, fstep = FS) known at compile time (candidate scan unrolled);
+// SPT: consecutive template states owned by one thread (thread i: states i*SPT .. i*SPT+SPT-1), so a
+// CTA of <= 1024 threads covers templates of up to 1024*SPT frames and a thread exchanges only its
+// window edges with its neighbours.
+template <int BITS, int TT, int MAXT, int MINB, int DT, int BS, int FS, int SPT>
 __global__ void __launch_bounds__(MAXT, MINB)
 dtw_fused_kernel(const double* __restrict__ tmplT, const int64_t* __restrict__ toff,
                  const double* __restrict__ seq, const int64_t* __restrict__ soff,
@@ -59,22 +65,22 @@ dtw_fused_kernel(const double* __restrict__ tmplT, const int64_t* __restrict__ t
                  int bstep_rt, int64_t* __restrict__ paths, double* __restrict__ final_cost) {
     constexpr int PER = 32 / BITS;
     constexpr uint32_t MASK = (BITS == 32) ? 0xFFFFFFFFu : ((1u << BITS) - 1u);
+    static_assert(TT % 2 == 0, "sequence tiles are read as double2");
     const int D = DT > 0 ? DT : Drt;
     const int bstep = BS >= 0 ? BS : bstep_rt, fstep = BS >= 0 ? FS : fstep_rt;
     const int p = blockIdx.x;
     const int64_t tb = toff[p], sb = soff[p];
     const int S = (int)(toff[p + 1] - tb);
     const int T = (int)(soff[p + 1] - sb);
-    const int i = threadIdx.x;
-    const bool active = i < S;
+    const int s0 = threadIdx.x * SPT;            // first state of this thread
     const int Spad = (S + 31) & ~31;
     uint32_t* bpp = bp + bpoff[p];  // [ceil(T/PER)][Spad]
 
     // cost columns carry `bstep` sentinels (+inf) on the left and `fstep` on the right, so the
     // candidate scan needs no range checks: an infinite candidate never passes the strict `<`
     extern __shared__ double smem[];
-    const int colw = bstep + (int)blockDim.x + fstep;
-    double* cur = smem + bstep;                  // [-bstep, blockDim + fstep)
+    const int colw = (bstep + (int)blockDim.x * SPT + fstep + 1) & ~1;
+    double* cur = smem + bstep;                  // [-bstep, blockDim*SPT + fstep)
     double* nxt = smem + colw + bstep;
     double* vt = smem + 2 * colw;                // [D][TT]  sequence tile, k-major (even offset: 16-byte aligned)
     __shared__ double red_v[32];
@@ -82,11 +88,15 @@ dtw_fused_kernel(const double* __restrict__ tmplT, const int64_t* __restrict__ t
     __shared__ int s_best;
     const double kInf = __longlong_as_double(0x7FF0000000000000LL);
 
-    const double* tcol = tmplT + tb * D + i;  // element k at tcol[k * S]
+    const double* tcol = tmplT + tb * D + s0;  // element (k, state s0 + j) at tcol[k * S + j]
     for (int e = threadIdx.x; e < 2 * colw; e += blockDim.x) smem[e] = kInf;
     __syncthreads();
-    if (active) cur[i] = (double)(i + 1);      // src/dtw.jl:49  costtable[:,1] = 1:S
-    uint32_t word = 0;
+#pragma unroll
+    for (int j = 0; j < SPT; ++j)
+        if (s0 + j < S) cur[s0 + j] = (double)(s0 + j + 1);      // src/dtw.jl:49  costtable[:,1] = 1:S
+    uint32_t word[SPT];
+#pragma unroll
+    for (int j = 0; j < SPT; ++j) word[j] = 0;
 
     for (int t0 = 0; t0 < T; t0 += TT) {
         const int ncols = min(TT, T - t0);
@@ -97,23 +107,30 @@ dtw_fused_kernel(const double* __restrict__ tmplT, const int64_t* __restrict__ t
         }
         __syncthreads();
 
-        // ---- observation costs for TT frames: acc[c] = sum_k (v[c][k] - tmpl[k])^2 with k in
-        //      ascending order, no FMA (src/dtw.jl:33-35)
-        double acc[TT];
+        // ---- observation costs for TT frames: acc[j][c] = sum_k (v[c][k] - tmpl[k][s0+j])^2 with k
+        //      in ascending order, no FMA (src/dtw.jl:33-35)
+        double acc[SPT][TT];
 #pragma unroll
-        for (int c = 0; c < TT; ++c) acc[c] = 0.0;
-        if (active) {
+        for (int j = 0; j < SPT; ++j)
+#pragma unroll
+            for (int c = 0; c < TT; ++c) acc[j][c] = 0.0;
+        if (s0 < S) {
             const double* tp = tcol;
             auto kstep = [&](int k) {
-                const double tk = *tp;
+                double tk[SPT];
+#pragma unroll
+                for (int j = 0; j < SPT; ++j) tk[j] = (SPT == 1 || s0 + j < S) ? tp[j] : 0.0;
                 tp += S;
                 const double2* v2 = reinterpret_cast<const double2*>(vt + k * TT);
 #pragma unroll
                 for (int c = 0; c < TT; c += 2) {
                     const double2 v = v2[c >> 1];
-                    const double d0 = __dsub_rn(v.x, tk), d1 = __dsub_rn(v.y, tk);
-                    acc[c] = __dadd_rn(acc[c], __dmul_rn(d0, d0));
-                    acc[c + 1] = __dadd_rn(acc[c + 1], __dmul_rn(d1, d1));
+#pragma unroll
+                    for (int j = 0; j < SPT; ++j) {
+                        const double d0 = __dsub_rn(v.x, tk[j]), d1 = __dsub_rn(v.y, tk[j]);
+                        acc[j][c] = __dadd_rn(acc[j][c], __dmul_rn(d0, d0));
+                        acc[j][c + 1] = __dadd_rn(acc[j][c + 1], __dmul_rn(d1, d1));
+                    }
                 }
             };
             if (DT > 0) {
@@ -131,31 +148,53 @@ dtw_fused_kernel(const double* __restrict__ tmplT, const int64_t* __restrict__ t
         for (int c = 0; c < TT; ++c) {
             if (c < ncols) {
                 const int t = t0 + c;
-                if (active) {
-                    const double oc = acc[c];
-                    int code = bstep;  // minindex - i + bstep
-                    double minc = __dadd_rn(__dadd_rn(cur[i], oc), 1.0);
-                    if (BS >= 0) {
+                if constexpr (BS >= 0) {
+                    // the thread's window of the previous column, read once
+                    constexpr int WN = SPT + BS + FS;
+                    double win[WN];
 #pragma unroll
-                        for (int dj = -BS; dj <= FS; ++dj) {
-                            if (dj == 0) continue;  // same value as the initial candidate: never `<`
-                            double cand = __dadd_rn(cur[i + dj], oc);
-                            if (dj != -1) cand = __dadd_rn(cand, 2.0);
-                            if (cand < minc) { minc = cand; code = dj + BS; }
-                        }
-                    } else {
-                        for (int dj = -bstep; dj <= fstep; ++dj) {
-                            double cand = __dadd_rn(cur[i + dj], oc);
-                            if (dj != -1) cand = __dadd_rn(cand, dj == 0 ? 1.0 : 2.0);
-                            if (cand < minc) { minc = cand; code = dj + bstep; }
+                    for (int e = 0; e < WN; ++e) win[e] = cur[s0 - BS + e];
+#pragma unroll
+                    for (int j = 0; j < SPT; ++j) {
+                        if (s0 + j < S) {
+                            const double oc = acc[j][c];
+                            int code = BS;  // minindex - i + bstep
+                            double minc = __dadd_rn(__dadd_rn(win[BS + j], oc), 1.0);
+#pragma unroll
+                            for (int dj = -BS; dj <= FS; ++dj) {
+                                if (dj == 0) continue;  // same value as the initial candidate: never `<`
+                                double cand = __dadd_rn(win[BS + j + dj], oc);
+                                if (dj != -1) cand = __dadd_rn(cand, 2.0);
+                                if (cand < minc) { minc = cand; code = dj + BS; }
+                            }
+                            nxt[s0 + j] = minc;
+                            word[j] |= (uint32_t)code << (BITS * (t % PER));
                         }
                     }
-                    nxt[i] = minc;
-                    word |= (uint32_t)code << (BITS * (t % PER));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < SPT; ++j) {
+                        const int i = s0 + j;
+                        if (i < S) {
+                            const double oc = acc[j][c];
+                            int code = bstep;
+                            double minc = __dadd_rn(__dadd_rn(cur[i], oc), 1.0);
+                            for (int dj = -bstep; dj <= fstep; ++dj) {
+                                double cand = __dadd_rn(cur[i + dj], oc);
+                                if (dj != -1) cand = __dadd_rn(cand, dj == 0 ? 1.0 : 2.0);
+                                if (cand < minc) { minc = cand; code = dj + bstep; }
+                            }
+                            nxt[i] = minc;
+                            word[j] |= (uint32_t)code << (BITS * (t % PER));
+                        }
+                    }
                 }
                 if ((t % PER) == PER - 1 || t == T - 1) {
-                    if (i < Spad) bpp[(int64_t)(t / PER) * Spad + i] = word;
-                    word = 0;
+#pragma unroll
+                    for (int j = 0; j < SPT; ++j) {
+                        if (s0 + j < Spad) bpp[(int64_t)(t / PER) * Spad + s0 + j] = word[j];
+                        word[j] = 0;
+                    }
                 }
                 __syncthreads();
                 double* tmp = cur; cur = nxt; nxt = tmp;
@@ -165,11 +204,18 @@ dtw_fused_kernel(const double* __restrict__ tmplT, const int64_t* __restrict__ t
 
     // ---- indmin(costtable[:, T+1]) -- first minimum  (src/dtw.jl:137)
     {
-        double v = active ? cur[i] : __longlong_as_double(0x7FF0000000000000LL);
-        int idx = active ? i : 0x7FFFFFFF;
-        // NaN never wins a `<` in the reference's scan unless it is first; keep it simple: treat
-        // NaN as +inf except at index 0 (cannot occur for finite inputs).
-        if (v != v && i != 0) v = __longlong_as_double(0x7FF0000000000000LL);
+        double v = kInf;
+        int idx = 0x7FFFFFFF;
+#pragma unroll
+        for (int j = 0; j < SPT; ++j) {
+            if (s0 + j < S) {
+                double vj = cur[s0 + j];
+                // NaN never wins a `<` in the reference's scan unless it is first; keep it simple: treat
+                // NaN as +inf except at index 0 (cannot occur for finite inputs).
+                if (vj != vj && s0 + j != 0) vj = kInf;
+                if (vj < v || idx == 0x7FFFFFFF) { v = vj; idx = s0 + j; }
+            }
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             double ov = __shfl_down_sync(0xFFFFFFFFu, v, o);
@@ -181,7 +227,7 @@ dtw_fused_kernel(const double* __restrict__ tmplT, const int64_t* __restrict__ t
         __syncthreads();
         if (w == 0) {
             const int nw = (blockDim.x + 31) >> 5;
-            v = (l < nw) ? red_v[l] : __longlong_as_double(0x7FF0000000000000LL);
+            v = (l < nw) ? red_v[l] : kInf;
             idx = (l < nw) ? red_i[l] : 0x7FFFFFFF;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -221,39 +267,43 @@ dtw_fused_kernel(const double* __restrict__ tmplT, const int64_t* __restrict__ t
     }
 }
 
+template <int BITS, int TT, int MAXT, int MINB, int DT, int BS, int FS, int SPT>
+static int32_t launch_dtw_cfg(const double* tmplT, const int64_t* d_toff, const double* seq,
+                              const int64_t* d_soff, const int64_t* d_bpoff, uint32_t* bp, int D,
+                              int fstep, int bstep, int64_t npairs, int maxS, int64_t* paths,
+                              double* final_cost, cudaStream_t st) {
+    const int nt = round_up((maxS + SPT - 1) / SPT, 32);
+    const int colw = round_up(bstep + nt * SPT + fstep, 2);
+    const size_t smem = (size_t)(2 * colw + D * TT) * sizeof(double);
+    auto k = dtw_fused_kernel<BITS, TT, MAXT, MINB, DT, BS, FS, SPT>;
+    VCB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)npairs, nt, smem, st>>>(tmplT, d_toff, seq, d_soff, d_bpoff, bp, D, fstep, bstep, paths, final_cost);
+    count_launch();
+    VCB_CUDA(cudaGetLastError());
+    return VCB_OK;
+}
+
 template <int BITS, int DT, int BS, int FS>
 static int32_t launch_dtw(const double* tmplT, const int64_t* d_toff, const double* seq,
                           const int64_t* d_soff, const int64_t* d_bpoff, uint32_t* bp, int D,
                           int fstep, int bstep, int64_t npairs, int maxS, int64_t* paths,
                           double* final_cost, cudaStream_t st) {
+#define VCB_DTW_ARGS tmplT, d_toff, seq, d_soff, d_bpoff, bp, D, fstep, bstep, npairs, maxS, paths, final_cost, st
     const int nt = round_up(maxS, 32);
-    const int colw = bstep + nt + fstep;
-    // <= 768 states: 16-column tiles (80-register budget); larger templates: 8-column tiles
     static const int two_ctas = [] { const char* e = getenv("VCB_DTW_2CTA"); return e ? atoi(e) : 1; }();
-    if (nt <= 672 && two_ctas && DT > 0) {   // (the runtime-dimension build would spill at 48 registers)
-        // two CTAs per SM (8-column tiles, 48 registers): one CTA's barrier-paced recurrence overlaps
-        // the other's FP64-bound observation costs
-        constexpr int TT = 8;
-        const size_t smem = (size_t)(2 * colw + 1 + D * TT) * sizeof(double);
-        auto k = dtw_fused_kernel<BITS, TT, 672, 2, DT, BS, FS>;
-        VCB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<(unsigned)npairs, nt, smem, st>>>(tmplT, d_toff, seq, d_soff, d_bpoff, bp, D, fstep, bstep, paths, final_cost);
-    } else if (nt <= 768) {
-        constexpr int TT = 16;
-        const size_t smem = (size_t)(2 * colw + 1 + D * TT) * sizeof(double);
-        auto k = dtw_fused_kernel<BITS, TT, 768, 1, DT, BS, FS>;
-        VCB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<(unsigned)npairs, nt, smem, st>>>(tmplT, d_toff, seq, d_soff, d_bpoff, bp, D, fstep, bstep, paths, final_cost);
-    } else {
-        constexpr int TT = 8;
-        const size_t smem = (size_t)(2 * colw + 1 + D * TT) * sizeof(double);
-        auto k = dtw_fused_kernel<BITS, TT, 1024, 1, DT, BS, FS>;
-        VCB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<(unsigned)npairs, nt, smem, st>>>(tmplT, d_toff, seq, d_soff, d_bpoff, bp, D, fstep, bstep, paths, final_cost);
-    }
-    count_launch();
-    VCB_CUDA(cudaGetLastError());
-    return VCB_OK;
+    // <= 672 states and a compile-time dimension: two CTAs per SM (8-column tiles, 48 registers): one
+    // CTA's barrier-paced recurrence overlaps the other's FP64-bound observation costs (the
+    // runtime-dimension build would spill at 48 registers)
+    if (nt <= 672 && two_ctas && DT > 0) return launch_dtw_cfg<BITS, 8, 672, 2, DT, BS, FS, 1>(VCB_DTW_ARGS);
+    // <= 768 states: 16-column tiles (80-register budget); up to 1024: 8-column tiles
+    if (nt <= 768) return launch_dtw_cfg<BITS, 16, 768, 1, DT, BS, FS, 1>(VCB_DTW_ARGS);
+    if (nt <= 1024) return launch_dtw_cfg<BITS, 8, 1024, 1, DT, BS, FS, 1>(VCB_DTW_ARGS);
+    // longer templates: several consecutive states per thread (the reference has no length limit,
+    // src/dtw.jl:93-98); the tile shrinks so that SPT * TT accumulators stay in registers
+    if (maxS <= 2048) return launch_dtw_cfg<BITS, 4, 1024, 1, DT, BS, FS, 2>(VCB_DTW_ARGS);
+    if (maxS <= 4096) return launch_dtw_cfg<BITS, 2, 1024, 1, DT, BS, FS, 4>(VCB_DTW_ARGS);
+    return launch_dtw_cfg<BITS, 2, 1024, 1, DT, BS, FS, 8>(VCB_DTW_ARGS);
+#undef VCB_DTW_ARGS
 }
 
 // Compile-time specialisations for the windows the reference uses (tests: bstep=1; align: bstep=2,
@@ -289,7 +339,8 @@ int32_t dtw_fit_batch_device(const double* d_tmpl, const int64_t* h_toff, const 
     for (int64_t p = 0; p < npairs; ++p) {
         const int64_t S = h_toff[p + 1] - h_toff[p], T = h_soff[p + 1] - h_soff[p];
         if (S < 1 || T < 1) return fail(VCB_EARG, "pair %lld has an empty template or sequence", (long long)p);
-        if (S > 1024) return fail(VCB_EUNSUPPORTED, "template of %lld frames: this build aligns templates of up to 1024 frames", (long long)S);
+        if (S > kDtwMaxStates)
+            return fail(VCB_EUNSUPPORTED, "template of %lld frames: one CTA holds the cost column of up to %d states", (long long)S, kDtwMaxStates);
         maxS = (int)std::max<int64_t>(maxS, S);
         bpoff[p + 1] = bpoff[p] + ((T + per - 1) / per) * ((S + 31) / 32 * 32);
     }
@@ -307,12 +358,14 @@ int32_t dtw_fit_batch_device(const double* d_tmpl, const int64_t* h_toff, const 
     VCB_CUDA(cudaMemcpyAsync(d_off, h_toff, noff * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     VCB_CUDA(cudaMemcpyAsync(d_off + noff, h_soff, noff * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     VCB_CUDA(cudaMemcpyAsync(d_off + 2 * noff, bpoff.data(), noff * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    stage_begin(st);
     {
         dim3 grid((unsigned)npairs, (maxS + 31) / 32), block(32, 8);
         dtw_transpose_kernel<<<grid, block, 0, st>>>(d_tmpl, d_off, d_tmplT, D);
         count_launch();
         VCB_CUDA(cudaGetLastError());
     }
+    stage_mark(st);      // [0] template transpose; [1] the fused kernel
     int32_t rc;
 #define VCB_DTW_CALL d_tmplT, d_off, d_seq, d_off + noff, d_off + 2 * noff, d_bp, D, fstep, bstep, npairs, maxS, d_paths, d_final_cost, st
     if (fstep == 0 && bstep == 1) rc = launch_dtw_dim<2, 1, 0>(VCB_DTW_CALL);
@@ -320,6 +373,7 @@ int32_t dtw_fit_batch_device(const double* d_tmpl, const int64_t* h_toff, const 
     else if (bits == 2) rc = launch_dtw_dim<2, -1, 0>(VCB_DTW_CALL);
     else if (bits == 4) rc = launch_dtw_dim<4, -1, 0>(VCB_DTW_CALL);
     else rc = launch_dtw_dim<8, -1, 0>(VCB_DTW_CALL);
+    stage_mark(st);
     cudaFreeAsync(d_off, st);
     cudaFreeAsync(d_tmplT, st);
     cudaFreeAsync(d_bp, st);

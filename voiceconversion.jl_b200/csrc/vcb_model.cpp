@@ -349,6 +349,7 @@ int32_t build_traj(const vcb_gmmmap& g, vcb_traj& t) {
     const int D2 = g.D, M = g.M;
     const size_t DD = (size_t)D2 * D2;
     t.g = &g;
+    t.device = g.device;
     t.Ds = D2 / 2;
     t.Dy.resize(DD * M);
     std::vector<double> d(DD), psym(DD * M);
@@ -368,7 +369,7 @@ int32_t build_traj(const vcb_gmmmap& g, vcb_traj& t) {
             for (int r = 0; r < D2; ++r)
                 psym[m * DD + r + (size_t)c * D2] = 0.5 * (d[r + (size_t)c * D2] + d[c + (size_t)r * D2]);
     }
-    if (t.d_P.upload(psym) != cudaSuccess)
+    if (t.d_P.upload(psym) != cudaSuccess || t.d_err.upload(std::vector<int>(1, 0)) != cudaSuccess)
         return fail(VCB_ECUDA, "model upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     return VCB_OK;
 }

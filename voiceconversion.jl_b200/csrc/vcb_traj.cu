@@ -497,7 +497,7 @@ int32_t traj_solve_device(const vcb_traj& tr, const double* dX, int64_t ldx, con
     if (Ds > 48) return fail(VCB_EUNSUPPORTED, "static dimension %d exceeds the trajectory solver's limit (48)", Ds);
 
     double *dE = nullptr, *dG = nullptr, *dL = nullptr, *dZ = nullptr;
-    int* derr = nullptr;
+    int* const derr = tr.d_err.p;   // sticky, read by the host entry points / vcb_traj_status
     VCB_CUDA(cudaMallocAsync((void**)&dE, (size_t)total * D2 * sizeof(double), st));
     VCB_CUDA(cudaMallocAsync((void**)&dG, (size_t)total * D2 * sizeof(double), st));
     // VCB_TRAJ_SOLVER=tiled keeps the 64-thread CTA solver for dimensions the warp solver covers
@@ -506,8 +506,6 @@ int32_t traj_solve_device(const vcb_traj& tr, const double* dX, int64_t ldx, con
     const size_t factor_bytes = std::max((size_t)3 * BB * sizeof(double), warp_bytes);
     VCB_CUDA(cudaMallocAsync((void**)&dL, (size_t)total * factor_bytes, st));
     VCB_CUDA(cudaMallocAsync((void**)&dZ, (size_t)total * Ds * sizeof(double), st));
-    VCB_CUDA(cudaMallocAsync((void**)&derr, sizeof(int), st));
-    VCB_CUDA(cudaMemsetAsync(derr, 0, sizeof(int), st));
     if (ws) {
         // frames bucketed by mixture: one Float64 GEMM per mixture panel (vcb_group.cu)
         VCB_TRY(group_e_step(tr, ws, npanels, dX, ldx, dE, dEy_out, dG, st));
@@ -521,6 +519,7 @@ int32_t traj_solve_device(const vcb_traj& tr, const double* dX, int64_t ldx, con
         count_launch();
         VCB_CUDA(cudaGetLastError());
     }
+    stage_mark(st);
     int32_t rc;
     {
         TrajParams p{};
@@ -537,11 +536,11 @@ int32_t traj_solve_device(const vcb_traj& tr, const double* dX, int64_t ldx, con
             default: rc = launch_tiled<6>(p, nchunks, st); break;
         }
     }
+    stage_mark(st);
     cudaFreeAsync(dE, st);
     cudaFreeAsync(dG, st);
     cudaFreeAsync(dL, st);
     cudaFreeAsync(dZ, st);
-    cudaFreeAsync(derr, st);
     return rc;
 }
 

@@ -36,6 +36,11 @@ def fit_batch(d: DTW, templates, tmpl_off, sequences, seq_off):
     to = np.ascontiguousarray(tmpl_off, dtype=np.int64)
     so = np.ascontiguousarray(seq_off, dtype=np.int64)
     n = len(to) - 1
+    nt = templates.shape[0] if hasattr(templates, "is_cuda") else np.shape(templates)[1]
+    ns = sequences.shape[0] if hasattr(sequences, "is_cuda") else np.shape(sequences)[1]
+    for off, total in ((to, nt), (so, ns)):
+        if off.ndim != 1 or len(off) != len(to) or n < 0 or (n > 0 and (off[0] < 0 or np.any(np.diff(off) < 0) or off[-1] > total)):
+            raise _lib.ArgumentError(_lib.EARG, "offsets must be (npairs+1,), non-decreasing and within the arrays")
     if hasattr(templates, "is_cuda"):
         import torch
         if templates.shape[1] != sequences.shape[1]:

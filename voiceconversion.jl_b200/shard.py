@@ -50,23 +50,36 @@ def shard_ragged(offsets: Sequence[int], rank: int, world: int, cost_fn: Callabl
     return (b, e), off[b:e + 1] - off[b]
 
 
-def gather_frames(local, dist=None, dst: int = 0):
+def gather_frames(local, dist=None, dst: int = 0, sizes: Sequence[int] = None):
     """Optional result gather to rank ``dst`` along the frame axis (axis 0 of a frame-major torch
-    tensor).  Uses ``torch.distributed`` (NCCL for CUDA tensors, gloo for CPU tensors); shards may
-    have different lengths.  Returns the concatenated tensor on ``dst`` and None elsewhere."""
+    tensor).  Every other rank sends its shard straight into its slice of ``dst``'s preallocated
+    batch (grouped ``isend``/``irecv``: ncclSend/ncclRecv over NVLink for CUDA tensors, gloo for CPU
+    tensors), so nothing is padded or copied twice; shards may have different lengths.
+    ``sizes`` (frames per rank) skips the size exchange when the caller knows the partition
+    (``shard_ragged`` is deterministic).  Returns the concatenated tensor on ``dst``, None elsewhere."""
     import torch
     if dist is None:
         import torch.distributed as dist  # noqa: PLW0642
     world, rank = dist.get_world_size(), dist.get_rank()
-    n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n)
-    sizes = [int(s.item()) for s in sizes]
-    maxn = max(sizes)
-    pad = torch.zeros((maxn,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    pad[: local.shape[0]] = local
-    bufs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(bufs, pad)
+    if sizes is None:
+        n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+        got = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(got, n)
+        sizes = [int(s.item()) for s in got]
+    sizes = [int(x) for x in sizes]
+    if len(sizes) != world or sizes[rank] != local.shape[0]:
+        raise ValueError("sizes must list the frame count of every rank")
     if rank != dst:
+        if sizes[rank] > 0:
+            for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, local.contiguous(), dst)]):
+                w.wait()
         return None
-    return torch.cat([bufs[r][: sizes[r]] for r in range(world)], dim=0)
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    out = torch.empty((int(starts[-1]),) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    ops = [dist.P2POp(dist.irecv, out[int(starts[r]):int(starts[r + 1])], r)
+           for r in range(world) if r != dst and sizes[r] > 0]
+    works = dist.batch_isend_irecv(ops) if ops else []
+    out[int(starts[dst]):int(starts[dst + 1])].copy_(local)
+    for w in works:
+        w.wait()
+    return out

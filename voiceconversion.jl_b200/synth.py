@@ -110,6 +110,36 @@ def trajectory_utterances(gmm: JointGMM, n_utt: int, frames: int | Tuple[int, in
     return fm, offsets
 
 
+def c4_utterances(gmm: JointGMM, utt_ids, frames: int, seed: int = 1004, rho: float = 0.9, seg: int = 20):
+    """Utterances of the C4 batch BY INDEX: utterance ``u`` depends only on ``(seed, u)``, so a rank
+    generates exactly its own shard of the 8192-utterance batch (same statistics as
+    ``trajectory_utterances``: piecewise-constant mixture sequence, AR(1)-smoothed excursions,
+    ``push_delta``).  Returns (fm (1+2Ds, n*frames) column-major, offsets (n+1,))."""
+    from scipy.signal import lfilter
+    utt_ids = np.asarray(utt_ids, dtype=np.int64)
+    Ds = gmm.means.shape[0] // 4
+    M = gmm.weights.shape[0]
+    Ls = np.stack([np.linalg.cholesky(gmm.covars[:Ds, :Ds, m]) for m in range(M)])
+    T = int(frames)
+    n = len(utt_ids)
+    offsets = (np.arange(n + 1, dtype=np.int64) * T)
+    fm = np.empty((1 + 2 * Ds, n * T), order="F")
+    nseg = (T + seg - 1) // seg
+    c = np.sqrt(1.0 - rho * rho)
+    for k, u in enumerate(utt_ids):
+        rng = np.random.default_rng([seed, int(u)])
+        comp = np.repeat(rng.choice(M, size=nseg, p=gmm.weights), seg)[:T]
+        eps = np.einsum("tij,tj->ti", Ls[comp], rng.standard_normal((T, Ds)))
+        drive = c * eps
+        drive[0] = eps[0]
+        noise = lfilter([1.0], [1.0, -rho], drive, axis=0)
+        static = (gmm.means[:Ds, comp].T + noise).T
+        b = k * T
+        fm[0, b:b + T] = rng.standard_normal(T)
+        fm[1:, b:b + T] = push_delta(np.asfortranarray(static))
+    return fm, offsets
+
+
 def dtw_pairs(n_pairs: int, dim: int, len_range: Tuple[int, int], seed: int, noise: float = 0.05):
     """Parallel-utterance pairs for ``DTWs.fit!``: template = smoothed random walk (dim, S);
     sequence = template resampled along a random monotone warp (local rate in [0.5, 2]) + noise.
