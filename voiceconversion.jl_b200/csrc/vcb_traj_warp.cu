@@ -20,6 +20,8 @@
 // streams 15 tiles (7.5 KB at NT = 3: Linv_t and L[t][t-1]) of factors to HBM for the back
 // substitution, which re-reads them once in fragment order (each lane reads exactly the bytes it
 // wrote); L[t][t-2] = -1/4 Pdd Linv' is not stored, its product is rebuilt there.
+#include <cstdlib>
+
 #include "vcb_kernels.h"
 #include "vcb_traj.h"
 
@@ -103,12 +105,18 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async16_cg(void* smem, const void* gmem) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(gmem) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // FULL: Ds == 8 NT (no padding, every 16-byte piece aligned): the 39 P tiles a step assembles its
 // R blocks from are prefetched into shared memory with cp.async during the previous step -- one
 // piece per lane and tile, read back only by the lane that requested it.
-template <int NT, bool FULL>
-__global__ void __launch_bounds__(32) traj_solve_warp(const TrajParams p) {
+template <int NT, bool FULL, int MINB = 1>
+__global__ void __launch_bounds__(32, MINB) traj_solve_warp(const TrajParams p) {
     using LY = WarpLayout<NT>;
     constexpr int DSP = LY::DSP, NL = LY::NL, NF = LY::NF, FT = LY::FT;
     const int lane = threadIdx.x, r = lane >> 2, q = lane & 3;
@@ -118,13 +126,20 @@ __global__ void __launch_bounds__(32) traj_solve_warp(const TrajParams p) {
     const int T = (int)(p.chunk_off[blockIdx.x + 1] - c0);
     if (T <= 0) return;
 
-    __shared__ __align__(16) double2 sLinv[2][NL][32];   // Linv_{t-1}, Linv_{t-2} by parity of t
-    __shared__ __align__(16) double2 sLp[NF][32];        // L[t-1][t-2]
+    // one pool of 512-byte tiles: Linv_{t-1}, Linv_{t-2} (by parity of t) | L[t-1][t-2] | FULL: the P
+    // tiles of the step (Pdd_{t-1}, Pds_{t-1}, Psd_t | Pss_t, Pdd_{t+1} lower); the back substitution
+    // reuses the pool as a ring of factor tiles
+    constexpr int NPT = 3 * NF + 2 * NL;
+    constexpr int NPOOL = 2 * NL + NF + (FULL ? NPT : 0);
+    __shared__ __align__(16) double2 pool[NPOOL][32];
+    double2(*const sLinv0)[32] = pool;
+    double2(*const sLp)[32] = pool + 2 * NL;
+    double2(*const sP)[32] = pool + (FULL ? 2 * NL + NF : 0);
     __shared__ __align__(16) double sdiag[64];
     __shared__ __align__(16) double sz[3][DSP];
     __shared__ __align__(16) double sw[DSP];
-    constexpr int NPT = 3 * NF + 2 * NL;                 // Pdd_{t-1}, Pds_{t-1}, Psd_t | Pss_t, Pdd_{t+1} (lower)
-    __shared__ __align__(16) double2 sP[FULL ? NPT : 1][32];
+    // FULL: r_t (the right-hand side row of the coming step), fetched by the same cp.async group as the P tiles
+    __shared__ __align__(16) double srow[FULL ? DSP : 2];
 
     const int32_t* mh = p.mhat + c0;
     const double* gv = p.Gv + c0 * D2;
@@ -133,6 +148,21 @@ __global__ void __launch_bounds__(32) traj_solve_warp(const TrajParams p) {
 
     for (int e = lane; e < 3 * DSP; e += 32) (&sz[0][0])[e] = 0.0;
     __syncwarp();
+    // power row of the chunk (src/common.jl:60): independent loads, all lanes, before the serial sweeps
+    if (p.copy_power)
+        for (int e = lane; e < T; e += 32) p.Y[(c0 + e) * p.ldy - 1] = p.Xpow[(c0 + e) * p.ldx - 1];
+    // FULL: r_t = u_t + 1/2 v_{t-1} - 1/2 v_{t+1} for the whole chunk, parked in the rows of Z that the
+    // forward sweep overwrites with z_t after it has consumed them
+    if (FULL) {
+        for (int e = lane; e < T * DSP; e += 32) {
+            const int t = e / DSP, k = e - t * DSP;
+            double v = gv[(size_t)t * D2 + k];
+            if (t >= 1) v = fma(0.5, gv[(size_t)(t - 1) * D2 + DSP + k], v);
+            if (t + 1 < T) v = fma(-0.5, gv[(size_t)(t + 1) * D2 + DSP + k], v);
+            Zg[e] = v;
+        }
+        __syncwarp();
+    }
     bool rok[NT], c0ok[NT], c1ok[NT];
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
@@ -155,10 +185,11 @@ __global__ void __launch_bounds__(32) traj_solve_warp(const TrajParams p) {
         return o;
     };
 
-    auto prefetch = [&](int tn) {
-        const double* Pa = p.P + (size_t)mh[tn >= 1 ? tn - 1 : 0] * D2 * D2 + lofs;
-        const double* Pb = p.P + (size_t)mh[tn] * D2 * D2 + lofs;
-        const double* Pc = p.P + (size_t)mh[tn + 1 < T ? tn + 1 : tn] * D2 * D2 + lofs;
+    // mixture indices of frames tn-1, tn, tn+1 come from registers (rolling window, loaded a step ahead)
+    auto prefetch = [&](int tn, int ma, int mb, int mc) {
+        const double* Pa = p.P + (size_t)ma * D2 * D2 + lofs;
+        const double* Pb = p.P + (size_t)mb * D2 * D2 + lofs;
+        const double* Pc = p.P + (size_t)mc * D2 * D2 + lofs;
         const size_t dd = (size_t)Ds * D2 + Ds, ds = (size_t)Ds * D2, sd = Ds;
 #pragma unroll
         for (int i = 0; i < NT; ++i)
@@ -173,24 +204,28 @@ __global__ void __launch_bounds__(32) traj_solve_warp(const TrajParams p) {
                     cp_async16(&sP[3 * NF + NL + LY::low(i, j)][lane], Pc + dd + o);
                 }
             }
+        if (lane < DSP / 2) cp_async16(&srow[2 * lane], Zg + (size_t)tn * DSP + 2 * lane);      // r_tn
         cp_async_commit();
     };
-    if (FULL) prefetch(0);
+    // m0 = mhat[t], m1 = mhat[t+1], m2 = mhat[t+2] (clamped to the chunk)
+    int m0 = mh[0], m1 = mh[T > 1 ? 1 : 0], m2 = mh[T > 2 ? 2 : T - 1];
+    if (FULL) prefetch(0, m0, m0, m1);
 
     // =========================== forward: block Cholesky + L z = r ===========================
     for (int t = 0; t < T; ++t) {
         const double* Pt = p.P + (size_t)mh[t] * D2 * D2;
         const double* Pm = (t >= 1) ? p.P + (size_t)mh[t - 1] * D2 * D2 : Pt;
         const double* Pp = (t + 1 < T) ? p.P + (size_t)mh[t + 1] * D2 * D2 : Pt;
-        const double2(*const Linv1)[32] = sLinv[(t + 1) & 1];
-        const double2(*const Linv2)[32] = sLinv[t & 1];
-        double2(*const LinvT)[32] = sLinv[t & 1];          // Linv_t replaces Linv_{t-2}
+        const double2(*const Linv1)[32] = sLinv0 + ((t + 1) & 1) * NL;
+        const double2(*const Linv2)[32] = sLinv0 + (t & 1) * NL;
+        double2(*const LinvT)[32] = sLinv0 + (t & 1) * NL;          // Linv_t replaces Linv_{t-2}
         double* const zt = sz[t % 3];
         const double* const z1 = sz[(t + 2) % 3];
         const double* const z2 = sz[(t + 1) % 3];
         double2* const F = Fb + (size_t)t * FT * 32;
-        double rr[NT];          // r_t = u_t + 1/2 v_{t-1} - 1/2 v_{t+1}, rows 8i + r (issued early, used in 4b)
-        {
+        const int m3 = mh[t + 3 < T ? t + 3 : T - 1];     // consumed by the next step's prefetch
+        double rr[NT];          // r_t = u_t + 1/2 v_{t-1} - 1/2 v_{t+1}, rows 8i + r
+        if (!FULL) {
             const double wm = (t >= 1) ? 0.5 : 0.0, wp = (t + 1 < T) ? -0.5 : 0.0;
             const double* g0 = gv + (size_t)t * D2, *gm = gv + (size_t)(t >= 1 ? t - 1 : t) * D2 + Ds;
             const double* gp = gv + (size_t)(t + 1 < T ? t + 1 : t) * D2 + Ds;
@@ -200,7 +235,12 @@ __global__ void __launch_bounds__(32) traj_solve_warp(const TrajParams p) {
                 if (rok[i]) rr[i] = fma(wp, gp[8 * i + r], fma(wm, gm[8 * i + r], g0[8 * i + r]));
             }
         }
-        if (FULL) cp_async_wait_all();
+        if (FULL) {
+            cp_async_wait_all();
+            __syncwarp();       // srow was requested by other lanes
+#pragma unroll
+            for (int i = 0; i < NT; ++i) rr[i] = srow[8 * i + r];
+        }
         auto Pddm = [&](int i, int j) { return FULL ? sP[i * NT + j][lane] : ldq(Pm, Ds, Ds, i, j); };
         auto Pdsm = [&](int i, int j) { return FULL ? sP[NF + i * NT + j][lane] : ldq(Pm, Ds, 0, i, j); };
         auto Psdt = [&](int i, int j) { return FULL ? sP[2 * NF + i * NT + j][lane] : ldq(Pt, 0, Ds, i, j); };
@@ -300,7 +340,7 @@ __global__ void __launch_bounds__(32) traj_solve_warp(const TrajParams p) {
                 }
                 S[LY::low(i, j)] = v;
             }
-        if (FULL && t + 1 < T) prefetch(t + 1);     // every tile of this step has been consumed
+        if (FULL && t + 1 < T) prefetch(t + 1, m0, m1, m2);     // every tile of this step has been consumed
         if (t >= 1) {
 #pragma unroll
             for (int j = 0; j < NT; ++j)
@@ -412,6 +452,7 @@ __global__ void __launch_bounds__(32) traj_solve_warp(const TrajParams p) {
                 LinvT[e][lane] = Li[e];
             }
         }
+        m0 = m1; m1 = m2; m2 = m3;
         __syncwarp();
     }
 
@@ -421,6 +462,155 @@ __global__ void __launch_bounds__(32) traj_solve_warp(const TrajParams p) {
     // L[t+2][t] = R[t+2][t] Linv_t' with R[t+2][t] = -1/4 Pdd_{t+1} symmetric, so
     // L[t+2][t]' y_{t+2} = Linv_t (R[t+2][t] y_{t+2}): two small mat-vecs with tiles that are already
     // here (Linv_t) or L2-resident (P) instead of 9 more factor tiles per frame from HBM.
+    if constexpr (FULL) {
+        // The serial chain of a step is short (two mat-vecs and their shuffle reductions), so the sweep
+        // runs at the speed its factor tiles arrive: they come through a ring of three steps of
+        // cp.async groups in the tile pool (Linv_t, L[t+1][t], z_t), requested three steps ahead.
+        double* const sy = &sz[0][0];   // ring of three, row-layout reads
+        double* const su = sdiag;       // u_t = R[t+2][t] y_{t+2}, prepared one step ahead
+        for (int e = lane; e < 3 * DSP; e += 32) sy[e] = 0.0;
+        for (int e = lane; e < DSP; e += 32) su[e] = 0.0;
+        cp_async_wait_all();
+        __syncwarp();
+        double2(*const ring)[32] = pool;
+        double* const zring = reinterpret_cast<double*>(pool + 3 * FT);
+        static_assert(3 * FT + 1 <= NPOOL || !FULL, "factor ring does not fit the tile pool");
+        auto bfetch = [&](int t) {
+            if (t >= 0) {
+                const double2* F = Fb + (size_t)t * FT * 32;
+                double2(*const slot)[32] = ring + (t % 3) * FT;
+#pragma unroll
+                for (int e = 0; e < NL; ++e) cp_async16_cg(&slot[e][lane], F + e * 32);
+                if (t + 1 < T) {
+#pragma unroll
+                    for (int e = 0; e < NF; ++e) cp_async16_cg(&slot[NL + e][lane], F + (FT + NL + e) * 32);
+                }
+                if (lane < DSP / 2) cp_async16_cg(zring + (t % 3) * DSP + 2 * lane, Zg + (size_t)t * DSP + 2 * lane);
+            }
+            cp_async_commit();
+        };
+        bfetch(T - 1); bfetch(T - 2); bfetch(T - 3);
+        int mcur = mh[T - 1], mnext = mh[T >= 2 ? T - 2 : 0];
+        for (int t = T - 1; t >= 0; --t) {
+            // P tiles behind u_{t-1} = -1/4 Pdd(mhat_t) y_{t+1}: requested now, consumed at the end of the step
+            const bool need_u = t >= 1 && t + 1 < T;
+            double2 Pd[NF];
+            if (need_u) {
+                const double* Pq = p.P + (size_t)mcur * D2 * D2;
+#pragma unroll
+                for (int i = 0; i < NT; ++i)
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) Pd[i * NT + j] = ldq(Pq, Ds, Ds, i, j);
+            }
+            const int mfar = mh[t >= 2 ? t - 2 : 0];
+            cp_async_wait_group<2>();       // the group of step t has landed (two younger ones may be in flight)
+            __syncwarp();                   // z_t was requested by other lanes
+            const double2(*const slot)[32] = ring + (t % 3) * FT;
+            const double* const zt = zring + (t % 3) * DSP;
+            const double* const y1 = sy + ((t + 1) % 3) * DSP;
+            double* const yt = sy + (t % 3) * DSP;
+            // v = Linv_t u_t
+            double v[NT];
+#pragma unroll
+            for (int i = 0; i < NT; ++i) v[i] = 0.0;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const double2 uc = *reinterpret_cast<const double2*>(su + 8 * j + 2 * q);
+#pragma unroll
+                for (int i = j; i < NT; ++i) {
+                    const double2 L = slot[LY::low(i, j)][lane];
+                    v[i] = fma(L.x, uc.x, fma(L.y, uc.y, v[i]));
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NT; ++i) {
+                v[i] += __shfl_xor_sync(kFull, v[i], 1);
+                v[i] += __shfl_xor_sync(kFull, v[i], 2);
+            }
+            // a = L[t+1][t]' y_{t+1}
+            double2 acc[NT];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) acc[j] = zero2();
+            if (t + 1 < T) {
+#pragma unroll
+                for (int i = 0; i < NT; ++i) {
+                    const double a = y1[8 * i + r];
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        const double2 A1 = slot[NL + i * NT + j][lane];
+                        acc[j].x = fma(A1.x, a, acc[j].x);
+                        acc[j].y = fma(A1.y, a, acc[j].y);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+#pragma unroll
+                for (int s = 4; s < 32; s <<= 1) {
+                    acc[j].x += __shfl_xor_sync(kFull, acc[j].x, s);
+                    acc[j].y += __shfl_xor_sync(kFull, acc[j].y, s);
+                }
+                if (r == 0) *reinterpret_cast<double2*>(sw + 8 * j + 2 * q) = acc[j];
+            }
+            __syncwarp();
+            double2 out[NT];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) out[j] = zero2();
+#pragma unroll
+            for (int i = 0; i < NT; ++i) {
+                const double w = zt[8 * i + r] - sw[8 * i + r] - v[i];
+#pragma unroll
+                for (int j = 0; j <= i; ++j) {
+                    const double2 L = slot[LY::low(i, j)][lane];
+                    out[j].x = fma(L.x, w, out[j].x);
+                    out[j].y = fma(L.y, w, out[j].y);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+#pragma unroll
+                for (int s = 4; s < 32; s <<= 1) {
+                    out[j].x += __shfl_xor_sync(kFull, out[j].x, s);
+                    out[j].y += __shfl_xor_sync(kFull, out[j].y, s);
+                }
+                if (r == 0) {
+                    *reinterpret_cast<double2*>(yt + 8 * j + 2 * q) = out[j];
+                    double* yg = p.Y + (c0 + t) * p.ldy + 8 * j + 2 * q;   // reshape(y, D, T)  src/trajectory_gmmmap.jl:109
+                    yg[0] = out[j].x;       // (rows of ldy = Ds + 1 doubles are not 16-byte aligned)
+                    yg[1] = out[j].y;
+                }
+            }
+            // u_{t-1} = -1/4 Pdd(mhat_t) y_{t+1}  (off the chain: y_{t+1} is one step old)
+            if (t >= 1) {
+                double u[NT];
+#pragma unroll
+                for (int i = 0; i < NT; ++i) u[i] = 0.0;
+                if (need_u) {
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        const double2 yc = *reinterpret_cast<const double2*>(y1 + 8 * j + 2 * q);
+#pragma unroll
+                        for (int i = 0; i < NT; ++i)
+                            u[i] = fma(-0.25 * Pd[i * NT + j].x, yc.x, fma(-0.25 * Pd[i * NT + j].y, yc.y, u[i]));
+                    }
+#pragma unroll
+                    for (int i = 0; i < NT; ++i) {
+                        u[i] += __shfl_xor_sync(kFull, u[i], 1);
+                        u[i] += __shfl_xor_sync(kFull, u[i], 2);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < NT; ++i)
+                    if (q == 0) su[8 * i + r] = u[i];
+            }
+            bfetch(t - 3);      // the slot of step t is free: all its reads are complete (warp-synchronous)
+            mcur = mnext;
+            mnext = mfar;
+            __syncwarp();
+        }
+        return;
+    }
+    // padded dimensions: tiles fetched one step ahead into registers
     double* const sy = &sz[0][0];   // ring of three, row-layout reads
 #pragma unroll
     for (int e = 0; e < 3 * DSP; e += 32)
@@ -533,7 +723,6 @@ __global__ void __launch_bounds__(32) traj_solve_warp(const TrajParams p) {
                 if (c1ok[j]) yg[1] = out[j].y;
             }
         }
-        if (p.copy_power && lane == 31) p.Y[(c0 + t) * p.ldy - 1] = p.Xpow[(c0 + t) * p.ldx - 1];  // src/common.jl:60
         __syncwarp();
     };
     {
@@ -553,6 +742,15 @@ __global__ void __launch_bounds__(32) traj_solve_warp(const TrajParams p) {
 
 template <int NT>
 int32_t launch_warp(const TrajParams& p, int64_t nchunks, cudaStream_t st) {
+    static const int occ = [] { const char* e = getenv("VCB_TRAJ_MINB"); return e ? atoi(e) : 0; }();
+    if (NT == 3 && occ) {      // occupancy experiment: direct P loads (11.5 KB shared memory), capped registers
+        auto k = occ >= 16 ? traj_solve_warp<NT, false, 16> : occ >= 12 ? traj_solve_warp<NT, false, 12> : traj_solve_warp<NT, false, 8>;
+        VCB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        k<<<(unsigned)nchunks, 32, 0, st>>>(p);
+        count_launch();
+        VCB_CUDA(cudaGetLastError());
+        return VCB_OK;
+    }
     if (p.Ds == 8 * NT) {
         auto k = traj_solve_warp<NT, true>;
         VCB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
