@@ -16,6 +16,7 @@ struct TrajParams {
     const double* Xpow; int64_t ldx; int copy_power;
     int Ds;
     int* err;
+    int role_rule;          // experiment switch of the two-warp solver (0 = default)
 };
 
 // Warp-per-chunk solver (vcb_traj_warp.cu): Ds <= 24.  Bytes of factor scratch per frame, 0 if the
