@@ -189,6 +189,34 @@ def measure_tf32_peak(torch):
         torch.backends.cuda.matmul.allow_tf32 = old
 
 
+def bind_near_gpu(torch, local: int) -> dict:
+    """Binds this rank to the CPUs local to its GPU (PCIe root / NUMA node) BEFORE any page-locked
+    buffer is allocated, so the staging memory is first-touched next to the device.  A container whose
+    cpuset excludes those CPUs keeps its affinity (reported)."""
+    info = {"bound": False, "cpus": None, "local_cpulist": None}
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        txt = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+        info["local_cpulist"] = txt
+        want = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                want.update(range(int(a), int(b) + 1))
+            elif part:
+                want.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        use = want & allowed
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            info["bound"] = True
+        info["cpus"] = len(os.sched_getaffinity(0))
+    except Exception as ex:
+        info["error"] = repr(ex)
+    return info
+
+
 def dtw_pairs_for_rank(vcb, rank: int):
     """1000 C3 pairs; rank r aligns its own, distinct set (seed 1003 + r)."""
     return vcb.synth.config_c3(1000, seed=1003 + rank)
@@ -294,6 +322,7 @@ class Ctx:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a B200: no CUDA device is visible and there is no CPU path")
         torch.cuda.set_device(self.local)
+        self.host = bind_near_gpu(torch, self.local) if self.world > 1 else {"bound": False, "cpus": host_cores()}
         vcb.set_device(self.local)
         vcb.set_kernel_variant(args.variant)
         if self.world > 1:
@@ -612,6 +641,7 @@ def main():
     clocks = sampler.stop() if ctx.rank == 0 else None
     if ctx.rank == 0:
         line["clocks"] = clocks
+        line["host"] = ctx.host
 
     # the other paths' complete sub-lines (same structure as a contract line), default run only
     if args.path == "fbf" and not args.skip_extras:

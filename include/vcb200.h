@@ -56,6 +56,19 @@ int32_t vcb_last_error(char* buf, size_t buflen);
 int32_t vcb_device_count(int32_t* count);
 /* Makes `device` current for this host thread (one process per GPU: call once with LOCAL_RANK). */
 int32_t vcb_set_device(int32_t device);
+/* Multi-device mode for ONE process driving several GPUs -- what a Julia caller of vc(mapper, fms)
+ * (bin/vc.jl:82) or of the batch align loop (bin/align.jl:84-113) gets: after vcb_init(ndev) (0 = all
+ * visible devices, 1 = back to single-device) the HOST-pointer batch entry points -- vcb_gmmmap_convert,
+ * vcb_gmmmap_vc, vcb_traj_convert_batch, vcb_traj_vc_batch, vcb_dtw_fit_batch, vcb_align_batch -- shard
+ * their batch over devices 0..ndev-1: contiguous ranges balanced by cost (frames / frames per utterance
+ * / cells per pair), one host thread and one copy/compute pipeline per device, the model replicated on
+ * each device on first use, no exchange between devices (every unit is independent: src/common.jl:17-19,
+ * :44-57, src/align.jl:16).  Small batches, the GV variant and all *_dev entry points stay on the
+ * handle's device.  Page-lock the caller's buffers (vcb_host_alloc / vcb_host_register) so that every
+ * device copies at PCIe speed. */
+int32_t vcb_init(int32_t ndev);
+/* Number of devices the host batch entry points currently shard over (1 = single-device mode). */
+int32_t vcb_num_devices(int32_t* n);
 /* Pinned host memory for zero-staging H2D/D2H (optional; any host pointer is accepted). */
 int32_t vcb_host_alloc(void** ptr, size_t bytes);
 int32_t vcb_host_free(void* ptr);

@@ -51,3 +51,35 @@ def test_vc_static_batch_fuses_push_delta(vcb, oracle):
     assert np.array_equal(outd, out)
     with pytest.raises(vcb.DimensionMismatch):
         vcb.vc_static_batch(t, fm, off)                             # already has delta rows
+
+
+def test_multi_device_mode_matches_single_device(vcb, oracle):
+    """vcb_init(n): the host batch entry points shard over the visible devices (one host thread and
+    pipeline per device, replicated model) and return exactly what one device returns.  With a single
+    visible GPU the call degenerates to single-device mode."""
+    ndev = vcb.device_count()
+    try:
+        assert vcb.init(0) == max(1, ndev)
+        gm, fm = vcb.synth.config_c1(ndev * 65536 + 777)
+        g = vcb.GMMMap(*gm)
+        multi = vcb.vc(g, fm)
+        gm2, fm2, off2 = vcb.synth.config_c2(4 * ndev + 3, 90)
+        # batches below the sharding threshold stay on one device; use a long one as well
+        big = np.asfortranarray(np.tile(fm2, (1, 48)))
+        boff = np.concatenate([[0], np.cumsum(np.tile(np.diff(off2), 48))]).astype(np.int64)
+        t = vcb.TrajectoryGMMMap(vcb.GMMMap(*gm2), 40)
+        tmulti, = vcb.vc_batch(t, big, boff, _split=False)
+        tm, to, sq, so = vcb.synth.dtw_pairs(8 * ndev + 1, 24, (60, 120), 5)
+        pmulti, cmulti = vcb.DTWs.fit_batch(vcb.DTWs.DTW(fstep=0, bstep=2), tm, to, sq, so)
+        amulti, _ = vcb.align_batch(tm, to, sq, so)
+        assert vcb.init(1) == 1
+        assert np.array_equal(multi, vcb.vc(g, fm))
+        tsingle, = vcb.vc_batch(vcb.TrajectoryGMMMap(vcb.GMMMap(*gm2), 40), big, boff, _split=False)
+        assert np.array_equal(tmulti, tsingle)
+        psingle, csingle = vcb.DTWs.fit_batch(vcb.DTWs.DTW(fstep=0, bstep=2), tm, to, sq, so)
+        assert np.array_equal(pmulti, psingle) and np.array_equal(cmulti, csingle)
+        assert np.array_equal(amulti, vcb.align_batch(tm, to, sq, so)[0])
+        ref, _ = oracle.dtw_fit_batch(tm, to, sq, so, 0, 2)
+        assert np.array_equal(pmulti, ref)
+    finally:
+        vcb.init(1)

@@ -24,7 +24,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (ArgumentError, CudaError, DimensionMismatch, PosDefException, SingularException,  # noqa: F401
-                   VCBError, device_count, launch_count, set_device, set_kernel_variant, stage_timing,
+                   VCBError, device_count, init, launch_count, set_device, set_kernel_variant, stage_timing,
                    stage_times)
 from . import dtws as DTWs  # noqa: N812  (Julia sub-module name, src/dtw.jl:1)
 from . import jld, shard, synth  # noqa: F401
@@ -35,7 +35,7 @@ __all__ = [
     "fvconvert", "fvconvert_gv", "vc", "vc_batch", "vc_static_batch", "ncomponents", "dim", "predict_proba",
     "predict", "constructW", "push_delta", "align", "align_batch", "DTWs", "DimensionMismatch",
     "PosDefException", "SingularException", "ArgumentError", "CudaError", "VCBError",
-    "set_device", "device_count", "set_kernel_variant", "launch_count", "traj_status",
+    "set_device", "device_count", "init", "set_kernel_variant", "launch_count", "traj_status",
 ]
 
 

@@ -60,6 +60,8 @@ SIGNATURES = {
     "vcb_last_error": (_i32, [C.c_char_p, C.c_size_t]),
     "vcb_device_count": (_i32, [C.POINTER(_i32)]),
     "vcb_set_device": (_i32, [_i32]),
+    "vcb_init": (_i32, [_i32]),
+    "vcb_num_devices": (_i32, [C.POINTER(_i32)]),
     "vcb_host_alloc": (_i32, [C.POINTER(_vp), C.c_size_t]),
     "vcb_host_free": (_i32, [_vp]),
     "vcb_host_register": (_i32, [_vp, C.c_size_t]),
@@ -147,6 +149,15 @@ def ptr(a) -> int:
 
 def set_device(device: int) -> None:
     check(lib().vcb_set_device(device))
+
+
+def init(ndev: int = 0) -> int:
+    """Multi-device mode: the host-array batch calls shard over devices 0..ndev-1 (0 = all visible,
+    1 = single device again).  Returns the number of devices in use."""
+    check(lib().vcb_init(int(ndev)))
+    n = _i32(0)
+    check(lib().vcb_num_devices(C.byref(n)))
+    return n.value
 
 
 def device_count() -> int:

@@ -2,9 +2,11 @@
 // host<->device staging and kernel selection.  No exception leaves this file.
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 
 #include "vcb_kernels.h"
 
@@ -13,6 +15,14 @@ namespace vcb {
 static thread_local std::string t_last_error;
 std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_variant{0};
+
+// multi-device mode (vcb_init): the devices the host batch entry points shard over
+static std::mutex g_devset_mu;
+static std::vector<int> g_devset;       // empty or one entry: single-device mode
+static std::vector<int> device_set() {
+    std::lock_guard<std::mutex> lk(g_devset_mu);
+    return g_devset;
+}
 
 namespace {
 // Ring of per-call event sets: the marks of up to kCalls consecutive calls stay readable, so a
@@ -252,6 +262,36 @@ int32_t vcb_device_count(int32_t* count) {
     return VCB_OK;
 }
 
+int32_t vcb_init(int32_t ndev) {
+    VCB_GUARD_BEGIN
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n < 1)
+        return fail(VCB_ECUDA, "no CUDA device available (%s); libvcb200 has no CPU path", cudaGetErrorString(e));
+    if (ndev < 0 || ndev > n) return fail(VCB_EARG, "vcb_init(%d): %d device(s) visible", ndev, n);
+    if (ndev == 0) ndev = n;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    std::vector<int> set;
+    for (int d = 0; d < ndev; ++d) {
+        VCB_CUDA(cudaSetDevice(d));
+        VCB_TRY(ensure_device());
+        set.push_back(d);
+    }
+    if (prev >= 0) cudaSetDevice(prev);
+    std::lock_guard<std::mutex> lk(g_devset_mu);
+    g_devset = set;
+    return VCB_OK;
+    VCB_GUARD_END
+}
+
+int32_t vcb_num_devices(int32_t* n) {
+    if (!n) return fail(VCB_EARG, "null argument");
+    const size_t k = device_set().size();
+    *n = k > 1 ? (int32_t)k : 1;
+    return VCB_OK;
+}
+
 int32_t vcb_set_device(int32_t device) {
     VCB_CUDA(cudaSetDevice(device));
     return ensure_device();
@@ -445,6 +485,101 @@ void pipe_release(HostPipe* p) {
 }
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------
+// Multi-device mode (vcb_init): the HOST-pointer batch entry points shard their batch over the
+// devices of the set -- contiguous ranges balanced by cost, one host thread + pipeline per device,
+// the model replicated on every device by K0, no data-path exchange.
+// ------------------------------------------------------------------------------------------------
+
+// Runs job(part, device) for every part on its own host thread with that device current (part 0 on the
+// calling thread) and returns the first failure; worker threads hand their error message to the caller.
+static int32_t run_on_devices(const std::vector<int>& devs, const std::function<int32_t(int, int)>& job) {
+    const int n = (int)devs.size();
+    std::vector<int32_t> rc(n, VCB_OK);
+    std::vector<std::string> msg(n);
+    auto body = [&](int part) {
+        if (cudaSetDevice(devs[part]) != cudaSuccess) {
+            rc[part] = VCB_ECUDA;
+            msg[part] = "cudaSetDevice failed in multi-device mode";
+            return;
+        }
+        rc[part] = ensure_device();
+        if (rc[part] == VCB_OK) {
+            try {
+                rc[part] = job(part, devs[part]);
+            } catch (const std::bad_alloc&) {
+                rc[part] = fail(VCB_ENOMEM, "out of host memory");
+            } catch (...) {
+                rc[part] = fail(VCB_EARG, "unexpected internal error");
+            }
+        }
+        if (rc[part] != VCB_OK) msg[part] = t_last_error;
+    };
+    int prev = -1;
+    cudaGetDevice(&prev);
+    std::vector<std::thread> th;
+    for (int part = 1; part < n; ++part) th.emplace_back(body, part);
+    body(0);
+    for (auto& t : th) t.join();
+    if (prev >= 0) cudaSetDevice(prev);
+    for (int part = 0; part < n; ++part)
+        if (rc[part] != VCB_OK) {
+            t_last_error = msg[part];
+            return rc[part];
+        }
+    return VCB_OK;
+}
+
+// The handle to use on `device`: the handle itself on its own device, else its replica (built once, by the
+// calling worker thread, with `device` current).
+static const vcb_gmmmap* gmmmap_on_device(const vcb_gmmmap& g, int device, int32_t* rc) {
+    *rc = VCB_OK;
+    if (device == g.device) return &g;
+    std::lock_guard<std::mutex> lk(g.rep_mu);
+    if ((int)g.replicas.size() <= device) g.replicas.resize(device + 1, nullptr);
+    if (!g.replicas[device]) {
+        vcb_gmmmap* r = new vcb_gmmmap();
+        r->device = device;
+        *rc = build_gmmmap(g.src_w.data(), g.src_mu.data(), g.src_sigma.data(), 2 * g.D, g.M, g.src_swap, *r);
+        if (*rc != VCB_OK) { delete r; return nullptr; }
+        r->src_w.clear(); r->src_mu.clear(); r->src_sigma.clear();
+        r->src_w.shrink_to_fit(); r->src_mu.shrink_to_fit(); r->src_sigma.shrink_to_fit();
+        g.replicas[device] = r;
+    }
+    return g.replicas[device];
+}
+static const vcb_traj* traj_on_device(const vcb_traj& t, int device, int32_t* rc) {
+    *rc = VCB_OK;
+    if (device == t.device) return &t;
+    const vcb_gmmmap* gr = gmmmap_on_device(*t.g, device, rc);
+    if (!gr) return nullptr;
+    std::lock_guard<std::mutex> lk(t.rep_mu);
+    if ((int)t.replicas.size() <= device) t.replicas.resize(device + 1, nullptr);
+    if (!t.replicas[device]) {
+        vcb_traj* r = new vcb_traj();
+        *rc = build_traj(*gr, *r);
+        if (*rc != VCB_OK) { delete r; return nullptr; }
+        t.replicas[device] = r;
+    }
+    return t.replicas[device];
+}
+
+// Contiguous split of n units into `parts` ranges of near-equal total cost (cost(i) >= 0).
+static std::vector<int64_t> split_by_cost(int64_t n, int parts, const std::function<double(int64_t)>& cost) {
+    std::vector<double> pre(n + 1, 0.0);
+    for (int64_t i = 0; i < n; ++i) pre[i + 1] = pre[i] + cost(i);
+    std::vector<int64_t> b(parts + 1, 0);
+    b[parts] = n;
+    for (int r = 1; r < parts; ++r) {
+        const double target = pre[n] * r / parts;
+        int64_t i = std::lower_bound(pre.begin(), pre.end(), target) - pre.begin();
+        i = std::min<int64_t>(std::max<int64_t>(i, b[r - 1]), n);
+        if (i > b[r - 1] && std::fabs(pre[i - 1] - target) <= std::fabs(pre[i] - target)) --i;
+        b[r] = i;
+    }
+    return b;
+}
+
 static int32_t fbf_host(const vcb_gmmmap& g, const double* X, int64_t T, int64_t ldx, double* Y,
                         int64_t ldy, bool whole_rows) {
     if (T == 0) return VCB_OK;
@@ -497,14 +632,32 @@ static int32_t fbf_host(const vcb_gmmmap& g, const double* X, int64_t T, int64_t
     return rc;
 }
 
+// Frames shard contiguously over the device set (src/common.jl:17-19: no state is carried from frame to
+// frame); small calls stay on the handle's device.
+static int32_t fbf_host_multi(const vcb_gmmmap& g, const double* X, int64_t T, int64_t ldx, double* Y, int64_t ldy,
+                              bool whole_rows) {
+    const std::vector<int> devs = device_set();
+    const int n = (int)devs.size();
+    if (n <= 1 || T < (int64_t)n * 65536) {
+        VCB_ON_DEVICE(g.device);
+        return fbf_host(g, X, T, ldx, Y, ldy, whole_rows);
+    }
+    return run_on_devices(devs, [&](int part, int dev) -> int32_t {
+        const int64_t b = T * part / n, e = T * (part + 1) / n;
+        int32_t rc;
+        const vcb_gmmmap* gd = gmmmap_on_device(g, dev, &rc);
+        if (!gd) return rc;
+        return fbf_host(*gd, X + b * ldx, e - b, ldx, Y + b * ldy, ldy, whole_rows);
+    });
+}
+
 int32_t vcb_gmmmap_convert(const vcb_gmmmap* g, const double* X, int32_t xrows, int64_t T, int64_t ldx,
                            double* Y, int64_t ldy) {
     VCB_GUARD_BEGIN
     if (!g || (T > 0 && (!X || !Y))) return fail(VCB_EARG, "null argument");
     if (xrows != g->D) return fail(VCB_EDIM, "Inconsistent dimentions. (frame has %d rows, dim(g) = %d)", xrows, g->D);
     if (T < 0 || ldx < xrows || ldy < xrows) return fail(VCB_EARG, "bad T/ld");
-    VCB_ON_DEVICE(g->device);
-    return fbf_host(*g, X, T, ldx, Y, ldy, false);
+    return fbf_host_multi(*g, X, T, ldx, Y, ldy, false);
     VCB_GUARD_END
 }
 
@@ -513,8 +666,7 @@ int32_t vcb_gmmmap_vc(const vcb_gmmmap* g, const double* fm, int32_t rows, int64
     if (!g || (T > 0 && (!fm || !out))) return fail(VCB_EARG, "null argument");
     if (rows != g->D + 1) return fail(VCB_EDIM, "Inconsistent dimentions. (feature matrix has %d rows, expected 1 + dim(g) = %d)", rows, g->D + 1);
     if (T < 0) return fail(VCB_EARG, "negative T");
-    VCB_ON_DEVICE(g->device);
-    return fbf_host(*g, fm + 1, T, rows, out + 1, rows, true);
+    return fbf_host_multi(*g, fm + 1, T, rows, out + 1, rows, true);
     VCB_GUARD_END
 }
 
@@ -675,9 +827,9 @@ static int32_t traj_host_slice(const vcb_traj& t, const double* X, int64_t ldx, 
 // chunks per SM) that rotate through the cached streams, so the H2D copy of slice i+1 and the D2H
 // copy of slice i-1 run under the kernels of slice i.  The band solver is latency-bound (its time
 // hardly depends on the number of chunks up to a full wave), so smaller slices would not pay.
-static int32_t traj_host(const vcb_traj& t, const double* X, int64_t ldx, const int64_t* offsets, int64_t nseq,
-                         int chunk_limit, double* Y, int64_t ldy, int64_t* mhat, double* Ey, bool whole_rows,
-                         GvRun gvr = GvRun()) {
+static int32_t traj_host_one(const vcb_traj& t, const double* X, int64_t ldx, const int64_t* offsets, int64_t nseq,
+                             int chunk_limit, double* Y, int64_t ldy, int64_t* mhat, double* Ey, bool whole_rows,
+                             GvRun gvr = GvRun()) {
     if (nseq == 0) return VCB_OK;
     if (offsets[0] < 0) return fail(VCB_EARG, "offsets must start at a non-negative frame");
     for (int64_t s = 0; s < nseq; ++s)
@@ -715,6 +867,30 @@ static int32_t traj_host(const vcb_traj& t, const double* X, int64_t ldx, const 
     return rc;
 }
 
+// Utterances shard contiguously over the device set, balanced by frames (every chunk is its own linear
+// system, src/common.jl:44-57); the GV variant and small batches stay on the handle's device.
+static int32_t traj_host(const vcb_traj& t, const double* X, int64_t ldx, const int64_t* offsets, int64_t nseq,
+                         int chunk_limit, double* Y, int64_t ldy, int64_t* mhat, double* Ey, bool whole_rows,
+                         GvRun gvr = GvRun()) {
+    const std::vector<int> devs = device_set();
+    const int n = (int)devs.size();
+    if (n <= 1 || gvr.gv || nseq < 2 * n || offsets[nseq] - offsets[0] < (int64_t)n * 16384) {
+        VCB_ON_DEVICE(t.device);
+        return traj_host_one(t, X, ldx, offsets, nseq, chunk_limit, Y, ldy, mhat, Ey, whole_rows, gvr);
+    }
+    for (int64_t s = 0; s < nseq; ++s)
+        if (offsets[s + 1] < offsets[s]) return fail(VCB_EARG, "offsets must be non-decreasing");
+    const std::vector<int64_t> cut = split_by_cost(nseq, n, [&](int64_t i) { return (double)(offsets[i + 1] - offsets[i]); });
+    return run_on_devices(devs, [&](int part, int dev) -> int32_t {
+        const int64_t b = cut[part], e = cut[part + 1];
+        if (e <= b) return VCB_OK;
+        int32_t rc;
+        const vcb_traj* td = traj_on_device(t, dev, &rc);
+        if (!td) return rc;
+        return traj_host_one(*td, X, ldx, offsets + b, e - b, chunk_limit, Y, ldy, mhat, Ey, whole_rows);
+    });
+}
+
 int32_t vcb_traj_convert_batch(const vcb_traj* t, const double* X, int32_t xrows, int64_t ldx,
                                const int64_t* offsets, int64_t nseq, int32_t chunk_limit, double* Y,
                                int64_t ldy, int64_t* mhat, double* Ey) {
@@ -722,7 +898,6 @@ int32_t vcb_traj_convert_batch(const vcb_traj* t, const double* X, int32_t xrows
     VCB_TRY(traj_check(t, xrows, ldx, offsets, nseq));
     if (!X || !Y) return fail(VCB_EARG, "null argument");
     if (ldy < t->Ds) return fail(VCB_EARG, "ldy < dim/2");
-    VCB_ON_DEVICE(t->device);
     return traj_host(*t, X, ldx, offsets, nseq, chunk_limit, Y, ldy, mhat, Ey, false);
     VCB_GUARD_END
 }
@@ -732,7 +907,6 @@ int32_t vcb_traj_vc_batch(const vcb_traj* t, const double* fm, int32_t rows, con
     VCB_GUARD_BEGIN
     VCB_TRY(traj_check(t, rows - 1, rows, offsets, nseq));
     if (!fm || !out) return fail(VCB_EARG, "null argument");
-    VCB_ON_DEVICE(t->device);
     return traj_host(*t, fm + 1, rows, offsets, nseq, chunk_limit, out + 1, t->Ds + 1, nullptr, nullptr, true);
     VCB_GUARD_END
 }
@@ -970,6 +1144,52 @@ int32_t vcb_dtw_fit_batch_dev(const double* dtmpl, const int64_t* tmpl_off, cons
     VCB_GUARD_END
 }
 
+// One device: pairs [0, npairs) described by tmpl_off / seq_off (absolute frame offsets into tmpl / seq).
+// Pairs are processed in slices on rotating streams, so the H2D copy of slice i+1 overlaps the kernel of slice i.
+static int32_t dtw_host_one(const double* tmpl, const int64_t* tmpl_off, const double* seq, const int64_t* seq_off,
+                            int64_t npairs, int D, int fstep, int bstep, int64_t* paths, double* final_cost) {
+    static const int64_t slice_pairs = [] { const char* e = getenv("VCB_DTW_SLICE"); return e ? atoll(e) : 296LL; }();
+    int dev = 0;
+    VCB_TRY(ensure_device(&dev));
+    HostPipe* hp = pipe_acquire(dev, 0, 0);
+    if (!hp) return fail(VCB_ECUDA, "stream creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    int32_t rc = VCB_OK;
+    int idx = 0;
+    for (int64_t p0 = 0; p0 < npairs && rc == VCB_OK; idx = (idx + 1) % kSlots) {
+        int64_t p1 = std::min(npairs, p0 + std::max<int64_t>(slice_pairs, 1));
+        if (npairs - p1 < slice_pairs / 2) p1 = npairs;          // no tiny tail slice
+        cudaStream_t st = hp->st[idx];
+        rc = [&]() -> int32_t {
+            const int64_t n = p1 - p0;
+            const int64_t tb = tmpl_off[p0], sb = seq_off[p0];
+            const int64_t nS = tmpl_off[p1] - tb, nT = seq_off[p1] - sb;
+            Scratch sc(st);
+            double *dT = nullptr, *dS = nullptr, *dC = nullptr;
+            int64_t* dP = nullptr;
+            VCB_CUDA(sc.get(&dT, (size_t)nS * D));
+            VCB_CUDA(sc.get(&dS, (size_t)nT * D));
+            VCB_CUDA(sc.get(&dP, (size_t)nT));
+            VCB_CUDA(sc.get(&dC, (size_t)n));
+            VCB_CUDA(cudaMemcpyAsync(dT, tmpl + tb * D, (size_t)nS * D * sizeof(double), cudaMemcpyHostToDevice, st));
+            VCB_CUDA(cudaMemcpyAsync(dS, seq + sb * D, (size_t)nT * D * sizeof(double), cudaMemcpyHostToDevice, st));
+            std::vector<int64_t> to(tmpl_off + p0, tmpl_off + p1 + 1), so(seq_off + p0, seq_off + p1 + 1);
+            for (auto& o : to) o -= tb;
+            for (auto& o : so) o -= sb;
+            VCB_TRY(dtw_fit_batch_device(dT, to.data(), dS, so.data(), n, D, fstep, bstep, dP, dC, st));
+            VCB_CUDA(cudaMemcpyAsync(paths + sb, dP, (size_t)nT * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+            if (final_cost)
+                VCB_CUDA(cudaMemcpyAsync(final_cost + p0, dC, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+            return VCB_OK;
+        }();
+        p0 = p1;
+    }
+    for (int s2 = 0; s2 < kSlots; ++s2)
+        if (cudaStreamSynchronize(hp->st[s2]) != cudaSuccess && rc == VCB_OK)
+            rc = fail(VCB_ECUDA, "DTW failed: %s", cudaGetErrorString(cudaGetLastError()));
+    pipe_release(hp);
+    return rc;
+}
+
 int32_t vcb_dtw_fit_batch(const double* tmpl, const int64_t* tmpl_off, const double* seq,
                           const int64_t* seq_off, int64_t npairs, int32_t D, int32_t fstep, int32_t bstep,
                           int64_t* paths, double* final_cost) {
@@ -977,27 +1197,20 @@ int32_t vcb_dtw_fit_batch(const double* tmpl, const int64_t* tmpl_off, const dou
     VCB_TRY(dtw_check(tmpl_off, seq_off, npairs, D));
     if (npairs == 0) return VCB_OK;
     if (!tmpl || !seq || !paths) return fail(VCB_EARG, "null argument");
-    VCB_TRY(ensure_device());
-    const int64_t tb = tmpl_off[0], sb = seq_off[0];
-    const int64_t nS = tmpl_off[npairs] - tb, nT = seq_off[npairs] - sb;
-    cudaStream_t st = nullptr;
-    Scratch sc(st);
-    double *dT = nullptr, *dS = nullptr, *dC = nullptr;
-    int64_t* dP = nullptr;
-    VCB_CUDA(sc.get(&dT, (size_t)nS * D));
-    VCB_CUDA(sc.get(&dS, (size_t)nT * D));
-    VCB_CUDA(sc.get(&dP, (size_t)nT));
-    VCB_CUDA(sc.get(&dC, (size_t)npairs));
-    VCB_CUDA(cudaMemcpyAsync(dT, tmpl + tb * D, (size_t)nS * D * sizeof(double), cudaMemcpyHostToDevice, st));
-    VCB_CUDA(cudaMemcpyAsync(dS, seq + sb * D, (size_t)nT * D * sizeof(double), cudaMemcpyHostToDevice, st));
-    std::vector<int64_t> to(tmpl_off, tmpl_off + npairs + 1), so(seq_off, seq_off + npairs + 1);
-    for (auto& o : to) o -= tb;
-    for (auto& o : so) o -= sb;
-    VCB_TRY(dtw_fit_batch_device(dT, to.data(), dS, so.data(), npairs, D, fstep, bstep, dP, dC, st));
-    VCB_CUDA(cudaMemcpyAsync(paths + sb, dP, (size_t)nT * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    if (final_cost) VCB_CUDA(cudaMemcpyAsync(final_cost, dC, (size_t)npairs * sizeof(double), cudaMemcpyDeviceToHost, st));
-    VCB_CUDA(cudaStreamSynchronize(st));
-    return VCB_OK;
+    for (int64_t p = 0; p < npairs; ++p)
+        if (tmpl_off[p + 1] < tmpl_off[p] || seq_off[p + 1] < seq_off[p]) return fail(VCB_EARG, "offsets must be non-decreasing");
+    const std::vector<int> devs = device_set();
+    const int n = (int)devs.size();
+    if (n <= 1 || npairs < 4 * n) return dtw_host_one(tmpl, tmpl_off, seq, seq_off, npairs, D, fstep, bstep, paths, final_cost);
+    // pairs shard contiguously over the device set, balanced by cells S*T (one DTW object per pair, src/align.jl:16)
+    const std::vector<int64_t> cut = split_by_cost(npairs, n, [&](int64_t i) {
+        return (double)(tmpl_off[i + 1] - tmpl_off[i]) * (double)(seq_off[i + 1] - seq_off[i]);
+    });
+    return run_on_devices(devs, [&](int part, int) -> int32_t {
+        const int64_t b = cut[part], e = cut[part + 1];
+        if (e <= b) return VCB_OK;
+        return dtw_host_one(tmpl, tmpl_off + b, seq, seq_off + b, e - b, D, fstep, bstep, paths, final_cost ? final_cost + b : nullptr);
+    });
     VCB_GUARD_END
 }
 
@@ -1056,12 +1269,8 @@ int32_t vcb_push_delta_batch(const double* src, int32_t D, const int64_t* offset
     VCB_GUARD_END
 }
 
-int32_t vcb_align_batch(const double* src, const int64_t* src_off, const double* tgt, const int64_t* tgt_off,
-                        int64_t npairs, int32_t D, double* newtgt, int64_t* paths) {
-    VCB_GUARD_BEGIN
-    VCB_TRY(dtw_check(src_off, tgt_off, npairs, D));
-    if (npairs == 0) return VCB_OK;
-    if (!src || !tgt || !newtgt) return fail(VCB_EARG, "null argument");
+static int32_t align_host_one(const double* src, const int64_t* src_off, const double* tgt, const int64_t* tgt_off,
+                              int64_t npairs, int D, double* newtgt, int64_t* paths) {
     VCB_TRY(ensure_device());
     const int64_t sb = src_off[0], tb = tgt_off[0];
     const int64_t nS = src_off[npairs] - sb, nT = tgt_off[npairs] - tb;
@@ -1088,6 +1297,28 @@ int32_t vcb_align_batch(const double* src, const int64_t* src_off, const double*
     if (paths) VCB_CUDA(cudaMemcpyAsync(paths + tb, dP, (size_t)nT * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     VCB_CUDA(cudaStreamSynchronize(st));
     return VCB_OK;
+}
+
+int32_t vcb_align_batch(const double* src, const int64_t* src_off, const double* tgt, const int64_t* tgt_off,
+                        int64_t npairs, int32_t D, double* newtgt, int64_t* paths) {
+    VCB_GUARD_BEGIN
+    VCB_TRY(dtw_check(src_off, tgt_off, npairs, D));
+    if (npairs == 0) return VCB_OK;
+    if (!src || !tgt || !newtgt) return fail(VCB_EARG, "null argument");
+    for (int64_t p = 0; p < npairs; ++p)
+        if (src_off[p + 1] < src_off[p] || tgt_off[p + 1] < tgt_off[p]) return fail(VCB_EARG, "offsets must be non-decreasing");
+    const std::vector<int> devs = device_set();
+    const int n = (int)devs.size();
+    if (n <= 1 || npairs < 4 * n) return align_host_one(src, src_off, tgt, tgt_off, npairs, D, newtgt, paths);
+    // the batch loop of bin/align.jl:84-113: pairs shard over the device set, balanced by cells
+    const std::vector<int64_t> cut = split_by_cost(npairs, n, [&](int64_t i) {
+        return (double)(src_off[i + 1] - src_off[i]) * (double)(tgt_off[i + 1] - tgt_off[i]);
+    });
+    return run_on_devices(devs, [&](int part, int) -> int32_t {
+        const int64_t b = cut[part], e = cut[part + 1];
+        if (e <= b) return VCB_OK;
+        return align_host_one(src, src_off + b, tgt, tgt_off + b, e - b, D, newtgt, paths);
+    });
     VCB_GUARD_END
 }
 

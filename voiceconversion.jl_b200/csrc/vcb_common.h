@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 #include <vector>
 
 #include "vcb200.h"
@@ -111,6 +112,18 @@ struct vcb_gmmmap {
     vcb::DevBuf<float> d_w32;
     vcb::DevBuf<float> d_c32;    // [M]
     vcb_tc_pack tc;
+    // multi-device mode (vcb_init): the joint parameters this handle was built from, and its replicas on
+    // the other devices (index = device ordinal; built on first use by that device's worker, owned here)
+    std::vector<double> src_w, src_mu, src_sigma;
+    int src_swap = 0;
+    mutable std::mutex rep_mu;
+    mutable std::vector<vcb_gmmmap*> replicas;
+    vcb_gmmmap() = default;
+    vcb_gmmmap(const vcb_gmmmap&) = delete;
+    vcb_gmmmap& operator=(const vcb_gmmmap&) = delete;
+    ~vcb_gmmmap() {
+        for (vcb_gmmmap* r : replicas) delete r;
+    }
 };
 
 struct vcb_traj;
@@ -131,4 +144,12 @@ struct vcb_traj {
     // definite).  Host entry points read and clear it after their synchronisation; *_dev callers
     // query it with vcb_traj_status.
     vcb::DevBuf<int> d_err;
+    mutable std::mutex rep_mu;                    // multi-device mode: replicas on the other devices
+    mutable std::vector<vcb_traj*> replicas;
+    vcb_traj() = default;
+    vcb_traj(const vcb_traj&) = delete;
+    vcb_traj& operator=(const vcb_traj&) = delete;
+    ~vcb_traj() {
+        for (vcb_traj* r : replicas) delete r;
+    }
 };

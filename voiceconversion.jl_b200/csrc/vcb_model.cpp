@@ -157,6 +157,10 @@ int32_t build_gmmmap(const double* weights, const double* mu, const double* sigm
     if (!(std::fabs(wsum - 1.0) <= 1.4901161193847656e-08 * std::fmax(std::fabs(wsum), 1.0)))
         return fail(VCB_EARG, "weights sum to %.17g, not a probability vector", wsum);
 
+    g.src_w.assign(weights, weights + M);
+    g.src_mu.assign(mu, mu + (size_t)twoD * M);
+    g.src_sigma.assign(sigma, sigma + (size_t)twoD * twoD * M);
+    g.src_swap = swap;
     g.w.assign(weights, weights + M);
     g.mux.resize((size_t)D * M);
     g.muy.resize((size_t)D * M);
