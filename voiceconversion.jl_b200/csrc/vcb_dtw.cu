@@ -20,6 +20,7 @@
 //
 // The template is read through a k-major ("transposed") copy so the per-k loads are coalesced.
 #include <cstdlib>
+#include <type_traits>
 
 #include "vcb_kernels.h"
 
@@ -283,6 +284,241 @@ static int32_t launch_dtw_cfg(const double* tmplT, const int64_t* d_toff, const 
     return VCB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Barrier-free variant for the reference's own windows (fstep = 0, bstep = 1 or 2): dependencies then
+// run one way only, from lower to higher template states, so the warps of a CTA form a PIPELINE.
+// A thread keeps the cost of its state in a register; the two neighbours below come by shuffle, and
+// lanes 0/1 take them from a small shared-memory ring in which every warp publishes the costs of its
+// last two states per column together with a progress counter.  Warp w runs about one column behind
+// warp w-1 and never meets a CTA-wide barrier, so the FP64 pipe is never drained by one (the
+// per-column __syncthreads of dtw_fused_kernel was its largest stall).  The sequence frames of a tile
+// are read as warp-uniform (L1-resident) global loads.  Bit-exact with the same candidate order.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire_shared(const volatile int* p) {
+    int v;
+    const unsigned a = (unsigned)__cvta_generic_to_shared(const_cast<const int*>(p));
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_shared(volatile int* p, int v) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(const_cast<int*>(p));
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
+template <int BITS, int TT, int REGS, int DT, int BS>
+__global__ void __maxnreg__(REGS)
+dtw_pipe_kernel(const double* __restrict__ tmplT, const int64_t* __restrict__ toff, const double* __restrict__ seq,
+                const int64_t* __restrict__ soff, const int64_t* __restrict__ bpoff, uint32_t* __restrict__ bp,
+                int64_t* __restrict__ paths, double* __restrict__ final_cost) {
+    constexpr int PER = 32 / BITS, R = 32;       // R: ring slots (columns a warp may run ahead of its consumer)
+    constexpr uint32_t MASK = (1u << BITS) - 1u;
+    static_assert(DT % 2 == 0 && (BS == 1 || BS == 2), "pipeline kernel: even dimension, bstep 1 or 2, fstep 0");
+    constexpr int D = DT;
+    const int p = blockIdx.x;
+    const int64_t tb = toff[p], sb = soff[p];
+    const int S = (int)(toff[p + 1] - tb);
+    const int T = (int)(soff[p + 1] - sb);
+    const int i = threadIdx.x, lane = i & 31, w = i >> 5, nw = blockDim.x >> 5;
+    const bool active = i < S;
+    const int Spad = (S + 31) & ~31;
+    uint32_t* bpp = bp + bpoff[p];
+    const double kInf = __longlong_as_double(0x7FF0000000000000LL);
+
+    extern __shared__ double smem[];
+    double* ring = smem;                                   // [nw][R][2]: costs of lanes 30, 31 after column t (slot t % R)
+    double* fin = smem + (size_t)nw * R * 2;               // [blockDim] final cost column
+    double* tiles = fin + blockDim.x;                      // [nw][2][TT][D] private double-buffered sequence tiles
+    volatile int* done = reinterpret_cast<volatile int*>(tiles + (size_t)nw * 2 * TT * D);   // [nw] latest published column
+    __shared__ double red_v[32];
+    __shared__ int red_i[32];
+    __shared__ int s_best;
+
+    double c = active ? (double)(i + 1) : kInf;            // src/dtw.jl:49  costtable[:,1] = 1:S
+    if (lane >= 30) ring[((size_t)w * R + 0) * 2 + (lane - 30)] = c;
+    if (lane == 0) done[w] = (32 * w < S) ? 0 : 0x7FFFFFFF;     // warps without a state never hold anyone up
+    __syncthreads();
+    if (32 * w < S) {
+        const double* tcol = tmplT + tb * D + i;           // element k at tcol[k * S]
+        const double* ring_prev = ring + (size_t)(w - 1) * R * 2;
+        double* ring_mine = ring + (size_t)w * R * 2;
+        const bool last_warp = 32 * (w + 1) >= S;          // nobody consumes this warp's boundary
+        int avail = 0;                                     // columns of warp w-1 known to be published
+        int room = R - 1;                                  // columns this warp may still publish without asking
+        uint32_t word = 0;
+        // the frames of a tile come through a private double buffer filled by cp.async one tile ahead (warps
+        // of the pipeline need a tile at different times, so there is no CTA-wide staging step)
+        double* const mytiles = tiles + (size_t)w * 2 * TT * D;
+        auto fetch_tile = [&](int t0n, int buf) {
+            if (t0n < T) {
+                const int pieces = min(TT, T - t0n) * (D / 2);
+                const double* src = seq + (sb + t0n) * D;
+                for (int e = lane; e < pieces; e += 32) {
+                    const unsigned a = (unsigned)__cvta_generic_to_shared(mytiles + (size_t)buf * TT * D + 2 * e);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(a), "l"(src + 2 * e) : "memory");
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        fetch_tile(0, 0);
+        for (int t0 = 0, tile = 0; t0 < T; t0 += TT, ++tile) {
+            const int ncols = min(TT, T - t0);
+            fetch_tile(t0 + TT, (tile + 1) & 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            __syncwarp();
+            // ---- observation costs for TT frames: strict left-to-right Float64 sum, no FMA (src/dtw.jl:33-35)
+            double acc[TT];
+#pragma unroll
+            for (int cc = 0; cc < TT; ++cc) acc[cc] = 0.0;
+            if (active) {
+                const double* tp = tcol;
+                const double2* vbase = reinterpret_cast<const double2*>(mytiles + (size_t)(tile & 1) * TT * D);
+#pragma unroll 2
+                for (int k2 = 0; k2 < D / 2; ++k2) {
+                    const double tk0 = tp[0], tk1 = tp[S];
+                    tp += 2 * S;
+#pragma unroll
+                    for (int cc = 0; cc < TT; ++cc) {
+                        const double2 v = vbase[cc * (D / 2) + k2];     // columns past the sequence: stale, unused
+                        const double d0 = __dsub_rn(v.x, tk0), d1 = __dsub_rn(v.y, tk1);
+                        acc[cc] = __dadd_rn(acc[cc], __dmul_rn(d0, d0));
+                        acc[cc] = __dadd_rn(acc[cc], __dmul_rn(d1, d1));
+                    }
+                }
+            }
+            // ---- column recurrence (src/dtw.jl:104-125): candidates i (stay), then i-bstep .. i-1, strict `<`
+#pragma unroll
+            for (int cc = 0; cc < TT; ++cc) {
+                if (cc < ncols) {
+                    const int t = t0 + cc;
+                    double b0 = kInf, b1 = kInf;           // costs of states 32w-2, 32w-1 after column t
+                    if (w > 0) {
+                        if (avail < t) {
+                            int a = ld_acquire_shared(done + w - 1);
+                            while (a < t) {
+                                __nanosleep(40);            // do not spend the issue slots of the working warps
+                                a = ld_acquire_shared(done + w - 1);
+                            }
+                            avail = a;
+                            __syncwarp();
+                        }
+                        if (lane < 2) {
+                            b0 = *reinterpret_cast<volatile const double*>(ring_prev + (size_t)(t % R) * 2);
+                            b1 = *reinterpret_cast<volatile const double*>(ring_prev + (size_t)(t % R) * 2 + 1);
+                        }
+                    }
+                    double c1 = __shfl_up_sync(0xFFFFFFFFu, c, 1);
+                    if (lane == 0) c1 = b1;
+                    const double oc = acc[cc];
+                    int code = BS;
+                    double minc = __dadd_rn(__dadd_rn(c, oc), 1.0);
+                    if (BS == 2) {
+                        double c2 = __shfl_up_sync(0xFFFFFFFFu, c, 2);
+                        if (lane == 0) c2 = b0;
+                        if (lane == 1) c2 = b1;
+                        const double cand = __dadd_rn(__dadd_rn(c2, oc), 2.0);
+                        if (cand < minc) { minc = cand; code = 0; }
+                    }
+                    {
+                        const double cand = __dadd_rn(c1, oc);     // transition 0: adding +0.0 is the identity
+                        if (cand < minc) { minc = cand; code = BS - 1; }
+                    }
+                    if (active) {
+                        c = minc;
+                        word |= (uint32_t)code << (BITS * (t % PER));
+                    }
+                    if ((t % PER) == PER - 1 || t == T - 1) {
+                        if (i < Spad) bpp[(int64_t)(t / PER) * Spad + i] = word;
+                        word = 0;
+                    }
+                    if (!last_warp) {
+                        if (room == 0) {                   // the slot about to be reused must have been consumed
+                            int a = ld_acquire_shared(done + w + 1);
+                            while (a < t + 2 - R) {
+                                __nanosleep(40);
+                                a = ld_acquire_shared(done + w + 1);
+                            }
+                            room = a - (t + 2 - R);
+                        } else {
+                            --room;
+                        }
+                        if (lane >= 30) ring_mine[(size_t)((t + 1) % R) * 2 + (lane - 30)] = c;
+                        __syncwarp();
+                    }
+                    // column t is consumed and column t+1 published: the counter serves the warp above as
+                    // "data ready" and the warp below as "slot free" (so the last warp counts as well)
+                    if (lane == 0) st_release_shared(done + w, t + 1);
+                }
+            }
+        }
+    }
+    fin[i] = c;
+    __syncthreads();
+
+    // ---- indmin(costtable[:, T+1]) -- first minimum  (src/dtw.jl:137)
+    {
+        double v = active ? fin[i] : kInf;
+        int idx = active ? i : 0x7FFFFFFF;
+        if (v != v && i != 0) v = kInf;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ov = __shfl_down_sync(0xFFFFFFFFu, v, o);
+            int oi = __shfl_down_sync(0xFFFFFFFFu, idx, o);
+            if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+        }
+        if (lane == 0) { red_v[w] = v; red_i[w] = idx; }
+        __syncthreads();
+        if (w == 0) {
+            v = (lane < nw) ? red_v[lane] : kInf;
+            idx = (lane < nw) ? red_i[lane] : 0x7FFFFFFF;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                double ov = __shfl_down_sync(0xFFFFFFFFu, v, o);
+                int oi = __shfl_down_sync(0xFFFFFFFFu, idx, o);
+                if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+            }
+            if (lane == 0) {
+                s_best = idx;
+                if (final_cost) final_cost[p] = v;
+            }
+        }
+        __syncthreads();
+    }
+    // ---- backward  (src/dtw.jl:139-142)
+    if (threadIdx.x < 32) {
+        int st = s_best;
+        int64_t* path = paths + sb;
+        if (lane == 0) path[T - 1] = st + 1;
+        int cur_wi = -1, wbase = 0;
+        uint32_t wd = 0;
+        for (int t = T - 1; t >= 1; --t) {
+            const int wi = t / PER;
+            if (wi != cur_wi || st < wbase || st >= wbase + 32) {
+                wbase = max(0, min(st - 31, Spad - 32));
+                wd = bpp[(int64_t)wi * Spad + wbase + lane];
+                cur_wi = wi;
+            }
+            const uint32_t ww = __shfl_sync(0xFFFFFFFFu, wd, st - wbase);
+            const int code = (int)((ww >> (BITS * (t % PER))) & MASK);
+            st = st + code - BS;
+            if (lane == 0) path[t - 1] = st + 1;
+        }
+    }
+}
+
+template <int BITS, int TT, int REGS, int DT, int BS>
+static int32_t launch_dtw_pipe(const double* tmplT, const int64_t* d_toff, const double* seq, const int64_t* d_soff,
+                               const int64_t* d_bpoff, uint32_t* bp, int64_t npairs, int maxS, int64_t* paths,
+                               double* final_cost, cudaStream_t st) {
+    const int nt = round_up(maxS, 32), nw = nt / 32;
+    const size_t smem = ((size_t)nw * 32 * 2 + nt + (size_t)nw * 2 * TT * DT) * sizeof(double) + (size_t)nw * sizeof(int);
+    auto k = dtw_pipe_kernel<BITS, TT, REGS, DT, BS>;
+    VCB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)npairs, nt, smem, st>>>(tmplT, d_toff, seq, d_soff, d_bpoff, bp, paths, final_cost);
+    count_launch();
+    VCB_CUDA(cudaGetLastError());
+    return VCB_OK;
+}
+
 template <int BITS, int DT, int BS, int FS>
 static int32_t launch_dtw(const double* tmplT, const int64_t* d_toff, const double* seq,
                           const int64_t* d_soff, const int64_t* d_bpoff, uint32_t* bp, int D,
@@ -291,10 +527,32 @@ static int32_t launch_dtw(const double* tmplT, const int64_t* d_toff, const doub
 #define VCB_DTW_ARGS tmplT, d_toff, seq, d_soff, d_bpoff, bp, D, fstep, bstep, npairs, maxS, paths, final_cost, st
     const int nt = round_up(maxS, 32);
     static const int two_ctas = [] { const char* e = getenv("VCB_DTW_2CTA"); return e ? atoi(e) : 1; }();
+    // VCB_DTW_PIPE=1: barrier-free warp pipeline for the reference's own windows (fstep 0, bstep 1 / 2) and
+    // an even compile-time dimension.  Bit-exact, but MEASURED SLOWER than the barrier kernel (C3: 4.41 vs
+    // 2.79 ms): passing the two boundary costs through shared-memory flags costs more per column (~350
+    // cycles: release store, acquire poll, ring read) than one __syncthreads of 21 warps (~100), and the
+    // warps of a CTA still move through observation and recurrence phases together.  Kept as an experiment.
+    static const int pipe = [] { const char* e = getenv("VCB_DTW_PIPE"); return e ? atoi(e) : 0; }();
+    if constexpr (DT > 0 && DT % 2 == 0 && FS == 0 && (BS == 1 || BS == 2) && BITS == 2) {
+        if (pipe && nt <= 672) return launch_dtw_pipe<BITS, 8, 48, DT, BS>(tmplT, d_toff, seq, d_soff, d_bpoff, bp, npairs, maxS, paths, final_cost, st);
+        if (pipe && nt <= 1024) return launch_dtw_pipe<BITS, 8, 64, DT, BS>(tmplT, d_toff, seq, d_soff, d_bpoff, bp, npairs, maxS, paths, final_cost, st);
+    }
     // <= 672 states and a compile-time dimension: two CTAs per SM (8-column tiles, 48 registers): one
     // CTA's barrier-paced recurrence overlaps the other's FP64-bound observation costs (the
     // runtime-dimension build would spill at 48 registers)
-    if (nt <= 672 && two_ctas && DT > 0) return launch_dtw_cfg<BITS, 8, 672, 2, DT, BS, FS, 1>(VCB_DTW_ARGS);
+    if (nt <= 672 && two_ctas && DT > 0) {
+        // experiment switch: states per thread / tile width / CTAs per SM for the common shape
+        static const int cfg = [] { const char* e = getenv("VCB_DTW_CFG"); return e ? atoi(e) : 0; }();
+        if constexpr (DT == 24 && BS == 2) {
+            if (cfg == 1 && maxS <= 704) return launch_dtw_cfg<BITS, 8, 352, 3, DT, BS, FS, 2>(VCB_DTW_ARGS);
+            if (cfg == 2 && maxS <= 704) return launch_dtw_cfg<BITS, 4, 352, 4, DT, BS, FS, 2>(VCB_DTW_ARGS);
+            if (cfg == 3 && maxS <= 704) return launch_dtw_cfg<BITS, 8, 352, 4, DT, BS, FS, 2>(VCB_DTW_ARGS);
+            if (cfg == 5 && maxS <= 704) return launch_dtw_cfg<BITS, 16, 352, 2, DT, BS, FS, 2>(VCB_DTW_ARGS);
+            if (cfg == 6 && maxS <= 704) return launch_dtw_cfg<BITS, 4, 192, 6, DT, BS, FS, 4>(VCB_DTW_ARGS);
+            if (cfg == 7 && maxS <= 704) return launch_dtw_cfg<BITS, 8, 192, 4, DT, BS, FS, 4>(VCB_DTW_ARGS);
+        }
+        return launch_dtw_cfg<BITS, 8, 672, 2, DT, BS, FS, 1>(VCB_DTW_ARGS);
+    }
     // <= 768 states: 16-column tiles (80-register budget); up to 1024: 8-column tiles
     if (nt <= 768) return launch_dtw_cfg<BITS, 16, 768, 1, DT, BS, FS, 1>(VCB_DTW_ARGS);
     if (nt <= 1024) return launch_dtw_cfg<BITS, 8, 1024, 1, DT, BS, FS, 1>(VCB_DTW_ARGS);
