@@ -94,6 +94,20 @@ def test_online_update(vcb, oracle):
     assert np.array_equal(vcb.DTWs.backward(d), ref)
 
 
+def test_fit_with_tables_matches_the_reference_state(vcb, oracle):
+    """fit!(d, template, sequence) leaves d.costtable / d.backpointer behind in the reference
+    (src/dtw.jl:122-127); fit(..., tables=True) reproduces them bit for bit."""
+    rng = np.random.default_rng(21)
+    tm, sq = rng.standard_normal((5, 33)), rng.standard_normal((5, 40))
+    d = vcb.DTWs.DTW(fstep=0, bstep=2)
+    p = vcb.DTWs.fit(d, tm, sq, tables=True)
+    o = oracle.DTW(fstep=0, bstep=2)
+    ref = o.fit(tm, sq)
+    c, b = o.tables()
+    assert np.array_equal(p, ref) and np.array_equal(d.costtable, c) and np.array_equal(d.backpointer, b)
+    assert np.array_equal(vcb.DTWs.fit(vcb.DTWs.DTW(fstep=0, bstep=2), tm, sq), ref)
+
+
 def test_device_entry_point(vcb, oracle):
     import torch
     tm, to, sq, so = vcb.synth.dtw_pairs(5, 24, (100, 140), 77)

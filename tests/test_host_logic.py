@@ -60,6 +60,33 @@ def test_jld_reader_on_reference_model(vcb, fixture_model):
     assert d2["diff"] is False and d2["covars"].shape == (80, 80, 32)
 
 
+def test_jld_writer_round_trip(vcb, fixture_model, tmp_path):
+    """jld.save writes the bin/train_gmm.jl:106-113 schema as the HDF5 subset of JLD v0.1; jld.load reads
+    it back bit for bit (both models of the reference's test/models when the checkout is present)."""
+    models = [("fixture", fixture_model, True)]
+    if os.path.exists(REF_MODEL):
+        for name in ("clb_to_slt_gmm32_order40_diff", "clb_and_slt_gmm32_order40"):
+            d = vcb.jld.load(REF_MODEL.replace("clb_to_slt_gmm32_order40_diff", name))
+            models.append((name, (d["weights"], d["means"], d["covars"]), d["diff"]))
+    for name, (w, mu, sg), diff in models:
+        p = tmp_path / (name + ".jld")
+        vcb.jld.save(str(p), w, mu, sg, diff=diff)
+        raw = p.read_bytes()
+        assert raw.startswith(b"Julia data file (HDF5), version 0.1.0") and raw[512:520] == b"\x89HDF\r\n\x1a\n"
+        e = vcb.jld.load(str(p))
+        assert np.array_equal(e["weights"], w) and np.array_equal(e["means"], mu) and np.array_equal(e["covars"], sg)
+        assert e["diff"] is bool(diff) and e["n_components"] == len(w)
+        assert e["means"].flags.f_contiguous and e["covars"].shape == (mu.shape[0], mu.shape[0], len(w))
+    # a random model with other sizes, and the schema check of the writer
+    gm = vcb.synth.random_joint_gmm(5, 3, 10)
+    p = tmp_path / "small.jld"
+    vcb.jld.save(str(p), *gm, diff=False, n_components=3)
+    e = vcb.jld.load(str(p))
+    assert np.array_equal(e["covars"], gm.covars) and e["diff"] is False
+    with pytest.raises(vcb.jld.JLDFormatError):
+        vcb.jld.save(str(p), gm.weights[:2], gm.means, gm.covars)
+
+
 def test_jld_reader_rejects_garbage(vcb, tmp_path):
     p = tmp_path / "x.jld"
     p.write_bytes(b"not hdf5" * 100)

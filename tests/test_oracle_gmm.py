@@ -84,3 +84,30 @@ def test_errors(oracle, vcb):
     assert e.value.code == oracle.EDIM
     with pytest.raises(oracle.OracleError):
         oracle.GMMMap(gm.weights * 2, gm.means, gm.covars)               # not a probability vector
+
+
+def test_vs_sklearn(oracle, fixture_model):
+    """Third, independent pin of predict_proba / predict (src/gmm.jl:24-58): scikit-learn's
+    GaussianMixture -- the library bin/train_gmm.jl:84-89 trains the reference's models with -- given
+    the fixture model's source marginal.  Its posterior comes from its own precision-Cholesky code
+    path (no shared code with the oracle or with scipy.stats)."""
+    from sklearn.mixture import GaussianMixture
+    from sklearn.mixture._gaussian_mixture import _compute_precision_cholesky
+    w, mu, sg = fixture_model
+    D, M = mu.shape[0] // 2, len(w)
+    z = np.load(os.path.join(GOLDEN, "fbf_c0.npz"))
+    X = np.asfortranarray(z["fm"][1:, :200])
+    gm = GaussianMixture(n_components=M, covariance_type="full")
+    gm.weights_ = w
+    gm.means_ = np.ascontiguousarray(mu[:D].T)
+    gm.covariances_ = np.ascontiguousarray(np.transpose(sg[:D, :D], (2, 0, 1)))
+    gm.precisions_cholesky_ = _compute_precision_cholesky(gm.covariances_, "full")
+    post = gm.predict_proba(X.T)                                  # (T, M)
+    g = oracle.GMMMap(w, mu, sg)
+    ours = np.stack([g.predict_proba(X[:, t]) for t in range(X.shape[1])])
+    assert np.abs(ours - post).max() < 1e-9
+    assert np.array_equal(g.predict(X), gm.predict(X.T) + 1)      # first maximum, 1-based
+    # and the conversion itself from sklearn's posterior: E[y|x] = sum_m p_m (mu_y + Syx Sxx^-1 (x - mu_x))
+    E = np.stack([mu[D:, m][:, None] + sg[D:, :D, m] @ np.linalg.solve(sg[:D, :D, m], X - mu[:D, m][:, None]) for m in range(M)])
+    y = np.einsum("tm,mdt->dt", post, E)
+    assert np.abs(g.vc(np.asfortranarray(z["fm"][:, :200]))[1:] - y).max() < 1e-9 * max(1.0, np.abs(y).max())

@@ -92,3 +92,32 @@ def test_golden_traj(oracle, vcb):
     g = oracle.GMMMap(*vcb.synth.random_joint_gmm(seed, M, jd))
     out = oracle.vc_traj_batch(g, int(z["limit"]), z["fm"], z["offsets"], nthreads=2)
     assert np.array_equal(out, z["out"])
+
+
+def test_vs_sparse_spsolve_at_c2_size(oracle, vcb):
+    """Literal SciPy-sparse transcription of src/trajectory_gmmmap.jl:82-109 at the C2/C4 chunk size
+    (static dimension 24, T = 500): W from the independent Python constructW, D^-1 = block_diag of the
+    LU-inverse Dy[:,:,mhat_t], and a general sparse direct solve of (W' D^-1 W) y = W' D^-1 E (SuperLU,
+    like the LU branch Julia's `\\` takes for this not exactly Hermitian matrix)."""
+    import scipy.sparse as sp
+    from scipy.sparse.linalg import spsolve
+    Ds, T, M = 24, 500, 8
+    gm = vcb.synth.random_joint_gmm(1002, M, 4 * Ds)
+    fm, off = vcb.synth.trajectory_utterances(gm, 1, T, 1002)
+    X = np.asfortranarray(fm[1:, :T])
+    g = oracle.GMMMap(*gm)
+    tg = oracle.TrajectoryGMMMap(g, T)
+    Y = tg.fvconvert(X)
+    # --- transcription
+    D2 = 2 * Ds
+    mu, sg = gm.means, gm.covars
+    mhat = g.predict(X) - 1                                                        # :82
+    A = [sg[D2:, :D2, m] @ np.linalg.inv(sg[:D2, :D2, m]) for m in range(M)]       # src/gmmmap.jl:34-36
+    Dy = [np.linalg.inv(sg[D2:, D2:, m] - A[m] @ sg[:D2, D2:, m]) for m in range(M)]   # :24-28
+    E = np.concatenate([mu[D2:, m] + A[m] @ (X[:, t] - mu[:D2, m]) for t, m in enumerate(mhat)])   # :85-91
+    Dinv = sp.block_diag([sp.csc_matrix(Dy[m]) for m in mhat], format="csc")      # :95-96
+    W = vcb.constructW(Ds, T)                                                      # :39-61
+    WtD = W.T @ Dinv                                                               # :103
+    y = spsolve((WtD @ W).tocsc(), WtD @ E)                                        # :105
+    ref = y.reshape(Ds, T, order="F")                                              # :109
+    assert np.abs(Y - ref).max() <= 1e-9 * np.abs(ref).max()

@@ -61,12 +61,24 @@ def fit_batch(d: DTW, templates, tmpl_off, sequences, seq_off):
     return paths, fc
 
 
-def fit(d: DTW, template, sequence=None) -> np.ndarray:
+def fit(d: DTW, template, sequence=None, tables: bool = False) -> np.ndarray:
     """``fit!(d, template, sequence)`` / ``fit!(d, sequence)``  (src/dtw.jl:93-130): the 1-based
-    template index aligned with every sequence frame."""
+    template index aligned with every sequence frame.
+
+    The fused kernel keeps the cost table on the chip, so ``d.costtable`` / ``d.backpointer`` are NOT
+    filled (the reference leaves its S x (T+1) tables behind, :122-123).  ``tables=True`` rebuilds them
+    exactly through ``update`` (one library call per frame) for callers that read them."""
     if sequence is None:
         template, sequence = d.template, template
     tm, sq = _f64(template), _f64(sequence)
+    if tables:
+        if tm.shape[0] != sq.shape[0]:
+            raise _lib.DimensionMismatch(_lib.EDIM, "template and sequence dimensions differ")
+        set_template(d, tm)
+        for t in range(sq.shape[1]):
+            update(d, sq[:, t])
+        d.final_cost = float(d.costtable[:, -1].min())
+        return backward(d)
     d.template = tm
     paths, fc = fit_batch(d, tm, [0, tm.shape[1]], sq, [0, sq.shape[1]])
     d.final_cost = float(fc[0])

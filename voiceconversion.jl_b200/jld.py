@@ -178,3 +178,117 @@ def load(path: str) -> Dict[str, object]:
         if k not in out:
             raise JLDFormatError(f"{path}: dataset '{k}' not found")
     return out
+
+
+# ---- writer ---------------------------------------------------------------------------------------
+def _pad8(b: bytes) -> bytes:
+    return b + b"\0" * (-len(b) % 8)
+
+
+def _msg(mtype: int, body: bytes, flags: int = 0) -> bytes:
+    body = _pad8(body)
+    return struct.pack("<HHB3x", mtype, len(body), flags) + body
+
+
+def _datatype_msg(dt: np.dtype) -> bytes:
+    if dt == np.dtype("<f8"):      # IEEE binary64, little endian: class 1 (floating point), version 1
+        return _msg(0x03, struct.pack("<B3BI", 0x11, 0x20, 63, 0, 8) + struct.pack("<HHBBBBI", 0, 64, 52, 11, 0, 52, 1023))
+    if dt == np.dtype("<i8"):      # class 0 (fixed point), signed
+        return _msg(0x03, struct.pack("<B3BI", 0x10, 0x08, 0, 0, 8) + struct.pack("<HH", 0, 64))
+    if dt == np.dtype("u1"):       # class 0, unsigned byte (the reader also accepts JLD's committed Bool type)
+        return _msg(0x03, struct.pack("<B3BI", 0x10, 0x00, 0, 0, 1) + struct.pack("<HH", 0, 8))
+    raise JLDFormatError(f"dtype {dt} not supported by the writer")
+
+
+def save(path: str, weights, means, covars, diff: bool = False, n_components: int = None) -> None:
+    """Writes a model in the schema of ``bin/train_gmm.jl:106-113`` (keys ``weights``, ``means``,
+    ``covars``, ``diff``, ``n_components``) as the HDF5 subset JLD v0.1 uses for plain arrays: 512-byte
+    user block with the JLD banner, superblock v0, one old-style root group (B-tree + local heap +
+    symbol node), v1 object headers, contiguous little-endian datasets whose HDF5 dimensions are the
+    reversed Julia dimensions (Julia writes its column-major memory as is).
+
+    ``load`` reads the result back bit for bit (tests/test_host_logic.py round-trips both models of
+    the reference's test/models).  The committed ``Bool`` datatype JLD attaches to ``diff`` and its
+    ``_creator`` group are bookkeeping of the Julia package and are not reproduced: ``diff`` is stored
+    as an unsigned byte.  Neither libhdf5 nor Julia exists in the build image, so reading these files
+    with JLD.jl itself is untested."""
+    w = np.ascontiguousarray(np.asarray(weights, dtype="<f8").reshape(-1))
+    mu = np.asfortranarray(np.asarray(means, dtype="<f8"))
+    sg = np.asfortranarray(np.asarray(covars, dtype="<f8"))
+    if mu.ndim != 2 or sg.ndim != 3 or sg.shape != (mu.shape[0], mu.shape[0], mu.shape[1]) or w.shape != (mu.shape[1],):
+        raise JLDFormatError("expected weights (M,), means (2D, M), covars (2D, 2D, M)")
+    M = mu.shape[1]
+    items = {      # name -> (HDF5 dims = reversed Julia dims, dtype, raw bytes in Julia memory order)
+        "covars": (sg.shape[::-1], np.dtype("<f8"), sg.tobytes(order="F")),
+        "diff": ((), np.dtype("u1"), bytes([1 if diff else 0])),
+        "means": (mu.shape[::-1], np.dtype("<f8"), mu.tobytes(order="F")),
+        "n_components": ((), np.dtype("<i8"), struct.pack("<q", M if n_components is None else int(n_components))),
+        "weights": (w.shape, np.dtype("<f8"), w.tobytes()),
+    }
+    names = sorted(items)                                   # symbol-node entries are ordered by name
+    LEAF_K, INTERNAL_K = 4, 16
+    if len(names) > 2 * LEAF_K:
+        raise JLDFormatError("too many datasets for one symbol node")
+    # ---- local heap data segment: offset 0 holds the empty string, names are 8-byte aligned
+    heap = bytearray(b"\0" * 8)
+    name_off = {}
+    for nme in names:
+        name_off[nme] = len(heap)
+        heap += _pad8(nme.encode() + b"\0")
+    free_off = len(heap)
+    heap += struct.pack("<QQ", 1, 32) + b"\0" * 16          # one free block (next = 1: end of list)
+    # ---- addresses (relative to the base address = size of the user block)
+    SUPER, ROOT_HDR = 0, 96
+    BTREE = ROOT_HDR + 16 + 24
+    btree_size = 24 + (2 * INTERNAL_K + 1) * 8 + 2 * INTERNAL_K * 8
+    HEAP = BTREE + btree_size
+    HEAP_DATA = HEAP + 32
+    SNOD = HEAP_DATA + len(heap)
+    pos = SNOD + 8 + 2 * LEAF_K * 40
+    hdr_addr, hdr_bytes, data_addr = {}, {}, {}
+    for nme in names:                                       # object headers first, raw data after them
+        dims, dt, raw = items[nme]
+        hdr_addr[nme] = pos
+        space = _msg(0x01, struct.pack("<BBB5x", 1, len(dims), 0) + b"".join(struct.pack("<Q", d) for d in dims))
+        fill = _msg(0x05, struct.pack("<BBBB", 2, 2, 0, 0))
+        layout_len = len(_msg(0x08, struct.pack("<BBQQ", 3, 1, 0, 0)))
+        hdr_bytes[nme] = (space, _datatype_msg(dt), fill, layout_len)
+        pos += 16 + len(space) + len(_datatype_msg(dt)) + len(fill) + layout_len
+    for nme in names:
+        pos += -pos % 8
+        data_addr[nme] = pos
+        pos += len(items[nme][2])
+    eof = pos
+    # ---- assemble
+    BASE = 512
+    out = bytearray(BASE + eof)
+    banner = b"Julia data file (HDF5), version 0.1.0"
+    out[:len(banner)] = banner
+
+    def put(addr, b):
+        out[BASE + addr:BASE + addr + len(b)] = b
+
+    undef = 0xFFFFFFFFFFFFFFFF
+    sb = _SIG + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, LEAF_K, INTERNAL_K, 0)
+    sb += struct.pack("<QQQQ", BASE, undef, BASE + eof, undef)
+    sb += struct.pack("<QQII", 0, ROOT_HDR, 1, 0) + struct.pack("<QQ", BTREE, HEAP)     # root entry caches B-tree / heap
+    put(SUPER, sb)
+    symtab = _msg(0x11, struct.pack("<QQ", BTREE, HEAP))
+    put(ROOT_HDR, struct.pack("<BBHII4x", 1, 0, 1, 1, len(symtab)) + symtab)
+    bt = b"TREE" + struct.pack("<BBHQQ", 0, 0, 1, undef, undef)
+    bt += struct.pack("<Q", 0) + struct.pack("<Q", SNOD) + struct.pack("<Q", name_off[names[-1]])
+    put(BTREE, bt)
+    put(HEAP, b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap), free_off, HEAP_DATA))
+    put(HEAP_DATA, bytes(heap))
+    sn = b"SNOD" + struct.pack("<BBH", 1, 0, len(names))
+    for nme in names:
+        sn += struct.pack("<QQII16x", name_off[nme], hdr_addr[nme], 0, 0)
+    put(SNOD, sn)
+    for nme in names:
+        space, dtm, fill, _ = hdr_bytes[nme]
+        layout = _msg(0x08, struct.pack("<BBQQ", 3, 1, data_addr[nme], len(items[nme][2])))
+        body = space + dtm + fill + layout
+        put(hdr_addr[nme], struct.pack("<BBHII4x", 1, 0, 4, 1, len(body)) + body)
+        put(data_addr[nme], items[nme][2])
+    with open(path, "wb") as f:
+        f.write(bytes(out))

@@ -15,6 +15,7 @@
 module VoiceConversionB200
 
 using Libdl
+using SparseArrays
 import Base: length, size
 
 export FrameByFrameConverter, TrajectoryConverter, GMMMapParam, GMMMap, TrajectoryGMMMap,
@@ -46,6 +47,16 @@ import LinearAlgebra
 
 # one process per GPU: call once with the local rank
 set_device(dev::Integer) = check(ccall((:vcb_set_device, libvcb200), Int32, (Int32,), dev))
+
+# ONE Julia process driving the whole box: after init(0) the batch methods below -- vc(mapper, fms),
+# fvconvert(g, X), DTWs.fit!(d, templates, toff, sequences, soff), align(srcs, tgts) -- shard their batch
+# over all visible GPUs inside the library (one host thread and copy pipeline per device, model replicated)
+function init(ndev::Integer=0)
+    check(ccall((:vcb_init, libvcb200), Int32, (Int32,), ndev))
+    n = Ref{Int32}(0)
+    check(ccall((:vcb_num_devices, libvcb200), Int32, (Ref{Int32},), n))
+    Int(n[])
+end
 
 # ---- type hierarchy (src/common.jl:2-4) -----------------------------------------------------------
 abstract type AbstractConverter end
@@ -88,6 +99,11 @@ mutable struct GMMMap <: FrameByFrameConverter
         g
     end
 end
+
+# model files: `load(path)` of JLD / JLD2 returns a Dict with the keys of bin/train_gmm.jl:106-113
+# ("weights", "means", "covars", "diff", "n_components"); bin/vc.jl:49-54 passes three of them on
+GMMMap(gmm::AbstractDict; swap::Bool=false) =
+    GMMMap(Vector{Float64}(gmm["weights"]), Matrix{Float64}(gmm["means"]), Array{Float64,3}(gmm["covars"]); swap=swap)
 
 length(g::GMMMap) = 1                      # src/gmmmap.jl:93
 dim(g::GMMMap) = g.D                       # :94
@@ -137,6 +153,26 @@ mutable struct TrajectoryGMMMap <: TrajectoryConverter
         finalizer(x -> ccall((:vcb_traj_destroy, libvcb200), Int32, (Ptr{Cvoid},), x.handle), t)
         t
     end
+end
+
+# constructW(D, T) (src/trajectory_gmmmap.jl:39-61): the sparse (2DT x DT) window matrix.  The library never
+# builds it (R = W' D^-1 W is assembled on the fly); it exists because the reference exposes and tests it
+# (test/trajectory_gmmmap.jl:1-34, 53).
+function constructW(D::Int, T::Int)
+    I_, J_, V_ = Int[], Int[], Float64[]
+    for t in 1:T
+        r0 = 2D * (t - 1)
+        for k in 1:D
+            push!(I_, r0 + k); push!(J_, (t - 1) * D + k); push!(V_, 1.0)                  # static: I at (t, t)
+            if t >= 2
+                push!(I_, r0 + D + k); push!(J_, (t - 2) * D + k); push!(V_, -0.5)         # delta: -1/2 I at (t, t-1)
+            end
+            if t < T
+                push!(I_, r0 + D + k); push!(J_, t * D + k); push!(V_, 0.5)                # delta: +1/2 I at (t, t+1)
+            end
+        end
+    end
+    sparse(I_, J_, V_, 2D * T, D * T)
 end
 
 length(t::TrajectoryGMMMap) = t.T                  # :34
@@ -237,6 +273,11 @@ function vc(c::TrajectoryGVGMMMap, fms::Vector{Matrix{Float64}})
     check(ccall((:vcb_trajgv_vc_batch, libvcb200), Int32,
                 (Ptr{Cvoid}, Ptr{Float64}, Int32, Ptr{Int64}, Int64, Int32, Int32, Float64, Ptr{Float64}),
                 c.handle, fm, rows, off, length(fms), limit, 100, 1.0e-5, out))
+    Tlast = size(fms[end], 2)
+    if Tlast > 0                                   # fvconvert(tgv, X) rebuilds tgmm.W for the last chunk (:153-156)
+        r = Tlast % limit
+        c.tgmm.T = r == 0 ? min(limit, Tlast) : r
+    end
     [out[:, off[i]+1:off[i+1]] for i in 1:length(fms)]
 end
 vc(c::TrajectoryGVGMMMap, fm::AbstractMatrix{Float64}) = vc(c, [Matrix{Float64}(fm)])[1]
@@ -278,8 +319,18 @@ mutable struct DTW
 end
 DTW(; fstep=0, bstep=1) = DTW(fstep, bstep, zeros(1, 1), zeros(1, 1), zeros(Int, 1, 1))
 
-function fit!(d::DTW, template::Matrix{Float64}, sequence::Matrix{Float64})
+# fit!(d, template, sequence) (src/dtw.jl:93-128).  The fused kernel keeps the cost table on the chip, so
+# d.costtable / d.backpointer are NOT filled (the reference leaves its S x (T+1) tables behind, :122-123);
+# tables=true rebuilds them exactly through update! (one library call per frame) for callers that read them.
+function fit!(d::DTW, template::Matrix{Float64}, sequence::Matrix{Float64}; tables::Bool=false)
     size(template, 1) == size(sequence, 1) || throw(DimensionMismatch("Inconsistent dimentions."))
+    if tables
+        set_template!(d, template)
+        for t in 1:size(sequence, 2)
+            update!(d, sequence[:, t])
+        end
+        return backward(d)
+    end
     d.template = template
     path = Vector{Int}(undef, size(sequence, 2))
     check(ccall((:vcb_dtw_fit_batch, libvcb200), Int32,
