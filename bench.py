@@ -375,6 +375,37 @@ class Ctx:
         ms = self.max_over_ranks(s.elapsed_time(e) / steps)
         return ms, int(launches), (stages[stage_index] if len(stages) > (stage_index or 0) else None), stages
 
+    def copy_ceiling(self, mb: int = 200, reps: int = 5) -> dict:
+        """Platform ceiling of the end-to-end paths, measured live: every rank copies `mb` MB host->device and
+        `mb` MB device->host CONCURRENTLY from page-locked memory on two streams, all ranks at once (barrier),
+        max over ranks.  GB/s per direction per GPU; on a box whose GPUs share host links it falls with N."""
+        if getattr(self, "_ceiling", None) is not None:
+            return self._ceiling
+        torch = self.torch
+        n = mb << 20
+        hin = torch.empty(n, dtype=torch.uint8).pin_memory()
+        hout = torch.empty(n, dtype=torch.uint8).pin_memory()
+        din = torch.empty(n, dtype=torch.uint8, device="cuda")
+        dout = torch.empty(n, dtype=torch.uint8, device="cuda")
+        s0, s1 = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def once():
+            with torch.cuda.stream(s0):
+                din.copy_(hin, non_blocking=True)
+            with torch.cuda.stream(s1):
+                hout.copy_(dout, non_blocking=True)
+        once()
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            once()
+        s0.synchronize(); s1.synchronize()
+        dt = self.max_over_ranks((time.perf_counter() - t0) / reps)
+        self._ceiling = {"gbs_each_direction_per_gpu": n / dt / 1e9, "gbs_each_direction_all_gpus": self.world * n / dt / 1e9,
+                         "how": f"{mb} MB H2D + {mb} MB D2H concurrently per rank from pinned memory, all {self.world} rank(s) at once, "
+                                "slowest rank"}
+        return self._ceiling
+
     def pinned(self, arr_T):
         """(rows, T) column-major numpy view of a page-locked copy of arr_T (T, rows)."""
         t = self.torch.from_numpy(np.ascontiguousarray(arr_T)).pin_memory()
@@ -411,6 +442,7 @@ def run_fbf(ctx: Ctx, steps: int, warmup: int) -> dict:
     torch.cuda.synchronize()
     e2e_s = ctx.max_over_ranks((time.perf_counter() - t0) / e2e_steps)
     e2e_ok = bool(np.array_equal(hout[0], fm[0]))
+    ceiling = ctx.copy_ceiling()
     if ctx.rank != 0:
         return {}
     tf32_peak = measure_tf32_peak(torch)
@@ -427,7 +459,10 @@ def run_fbf(ctx: Ctx, steps: int, warmup: int) -> dict:
         "config": cfg,
         "e2e": {"value": ctx.world * T / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": in_bytes, "steps": e2e_steps, "power_row_ok": e2e_ok,
-                "note": "vc(g, fm) through the C ABI with pinned Float64 host buffers, pipelined H2D/kernel/D2H"},
+                "gbs_each_direction_per_gpu": in_bytes / e2e_s / 1e9, "copy_ceiling": ceiling,
+                "fraction_of_copy_ceiling": (in_bytes / e2e_s / 1e9) / ceiling["gbs_each_direction_per_gpu"],
+                "note": "vc(g, fm) through the C ABI with pinned Float64 host buffers, pipelined H2D/kernel/D2H; the path "
+                        "moves 16(D+1) B per frame each way, so host<->device copy bandwidth is its ceiling"},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
                      "frac": achieved / tf32_peak, "traffic": prof["traffic"],

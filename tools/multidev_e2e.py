@@ -9,7 +9,7 @@ import vcb200 as vcb
 
 paths = sys.argv[1:] or ["fbf", "traj", "dtw"]
 ndev = vcb.device_count()
-counts = [n for n in (1, 2, 4, 8) if n <= ndev]
+counts = [n for n in (int(c) for c in os.environ.get("COUNTS", "1,2,4,8").split(",")) if n <= ndev]
 
 
 def pinned(a_T):
