@@ -442,7 +442,28 @@ struct HostPipe {
     cudaStream_t st[kSlots] = {};
     double* din[kSlots] = {};
     double* dout[kSlots] = {};
+    // page-locked bounce buffer (grow-only) for small results bound for pageable caller memory: an async
+    // copy into pageable memory blocks the calling thread until the stream has drained, which would
+    // serialise the slices of the host pipelines
+    void* bounce = nullptr;
+    size_t bounce_bytes = 0;
+    void* bounce_for(size_t bytes) {
+        if (bytes > bounce_bytes) {
+            if (bounce) cudaFreeHost(bounce);
+            bounce = nullptr;
+            bounce_bytes = 0;
+            if (cudaHostAlloc(&bounce, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            bounce_bytes = bytes;
+        }
+        return bounce;
+    }
 };
+// true if `p` is page-locked (allocated or registered with CUDA): async copies to it do not block the caller
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
 std::mutex g_pipe_mu;
 std::vector<HostPipe*> g_pipe_pool;
 
@@ -1153,6 +1174,18 @@ static int32_t dtw_host_one(const double* tmpl, const int64_t* tmpl_off, const d
     VCB_TRY(ensure_device(&dev));
     HostPipe* hp = pipe_acquire(dev, 0, 0);
     if (!hp) return fail(VCB_ECUDA, "stream creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    // results go through the pipe's page-locked bounce buffer unless the caller's arrays are page-locked
+    const int64_t sb0 = seq_off[0], nT_all = seq_off[npairs] - sb0;
+    const bool direct = is_pinned(paths + sb0) && (!final_cost || is_pinned(final_cost));
+    int64_t* bpaths = nullptr;
+    double* bcost = nullptr;
+    if (!direct) {
+        void* b = hp->bounce_for((size_t)nT_all * sizeof(int64_t) + (size_t)npairs * sizeof(double));
+        if (b) {
+            bpaths = static_cast<int64_t*>(b);
+            bcost = reinterpret_cast<double*>(bpaths + nT_all);
+        }
+    }
     int32_t rc = VCB_OK;
     int idx = 0;
     for (int64_t p0 = 0; p0 < npairs && rc == VCB_OK; idx = (idx + 1) % kSlots) {
@@ -1176,9 +1209,10 @@ static int32_t dtw_host_one(const double* tmpl, const int64_t* tmpl_off, const d
             for (auto& o : to) o -= tb;
             for (auto& o : so) o -= sb;
             VCB_TRY(dtw_fit_batch_device(dT, to.data(), dS, so.data(), n, D, fstep, bstep, dP, dC, st));
-            VCB_CUDA(cudaMemcpyAsync(paths + sb, dP, (size_t)nT * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+            int64_t* hpaths = bpaths ? bpaths + (sb - sb0) : paths + sb;
+            VCB_CUDA(cudaMemcpyAsync(hpaths, dP, (size_t)nT * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
             if (final_cost)
-                VCB_CUDA(cudaMemcpyAsync(final_cost + p0, dC, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+                VCB_CUDA(cudaMemcpyAsync(bcost ? bcost + p0 : final_cost + p0, dC, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
             return VCB_OK;
         }();
         p0 = p1;
@@ -1186,6 +1220,10 @@ static int32_t dtw_host_one(const double* tmpl, const int64_t* tmpl_off, const d
     for (int s2 = 0; s2 < kSlots; ++s2)
         if (cudaStreamSynchronize(hp->st[s2]) != cudaSuccess && rc == VCB_OK)
             rc = fail(VCB_ECUDA, "DTW failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc == VCB_OK && bpaths) {
+        std::memcpy(paths + sb0, bpaths, (size_t)nT_all * sizeof(int64_t));
+        if (final_cost) std::memcpy(final_cost, bcost, (size_t)npairs * sizeof(double));
+    }
     pipe_release(hp);
     return rc;
 }
