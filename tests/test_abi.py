@@ -58,6 +58,25 @@ def test_no_cpu_fallback(vcb):
         vcb.DTWs.fit(vcb.DTWs.DTW(), np.zeros((2, 3)), np.zeros((2, 4)))
 
 
+def test_multi_device_and_profiling_entry_points_without_a_gpu(vcb):
+    """vcb_init needs a device (no CPU path); the stage-timing aid is inert until a device call ran."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("GPU present")
+    except ImportError:
+        pass
+    with pytest.raises(vcb.CudaError):
+        vcb.init(0)
+    L = vcb._lib.lib()
+    n = ctypes.c_int32(7)
+    assert L.vcb_num_devices(ctypes.byref(n)) == 0 and n.value == 1
+    vcb.stage_timing(True)
+    assert vcb.stage_times() == []
+    vcb.stage_timing(False)
+    assert L.vcb_traj_status(None, None) == vcb._lib.EARG
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "voiceconversion.jl_b200")
     for dirpath, _, files in os.walk(pkg):

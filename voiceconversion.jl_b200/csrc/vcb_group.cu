@@ -6,6 +6,8 @@
 // bucketed by mixture (counting sort, order inside a bucket irrelevant) and every CTA multiplies one
 // mixture's matrices, held in shared memory, with a 64-frame panel: a Float64 GEMM per mixture.
 // The same kernel serves the GV gradient (h_t = P_m (E_t - (W y)_t), src/trajectory_gmmmap.jl:161).
+#include <cstdlib>
+
 #include "vcb_kernels.h"
 
 namespace vcb {
@@ -237,6 +239,170 @@ __global__ void group_panel_kernel(const GroupParams p) {
     }
 }
 
+// ---- the same products on the FP64 tensor path (D2 <= 96) ---------------------------------------
+// One CTA = one 64-frame panel of one mixture, 8 warps; warp w owns the 8 frames [8w, 8w+8) and all
+// NI = ceil(D2/8) row tiles of the output, i.e. NI accumulator tiles of mma.sync.m8n8k4.f64.  Per
+// k-step a warp reads one B fragment (panel) and NI A fragments (matrix) from shared memory for NI DMMAs
+// (the register-tiled DFMA version needed 4 LDS.128 per 16 DFMA and sat at 25 % of the FP64 pipe).
+// Both matrices of the mixture arrive by cp.async while the panel is being gathered.  The E panel of
+// a warp's frames is produced and consumed by that warp alone, so no CTA barrier separates the two GEMMs.
+// Leading dimensions are = 8 (mod 16) doubles: the four k-columns of a fragment fall on distinct halves of
+// the banks (two wavefronts per 64-bit fragment load, the minimum).
+__device__ __forceinline__ void dmma_acc(double2& c, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c.x), "+d"(c.y) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16_g(void* smem, const void* gmem) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(gmem) : "memory");
+}
+
+template <int MODE, int NI>
+__global__ void __launch_bounds__(256) group_panel_dmma_kernel(const GroupParams p) {
+    constexpr int DP = 8 * NI, LDM = DP + 8, LDP = kFT + 8;
+    extern __shared__ __align__(16) double sm[];
+    double* matA = sm;                         // [DP][LDM]  A_m: column k at matA + k*LDM (MODE 0)
+    double* matP = matA + (MODE == 0 ? DP * LDM : 0);      // P_m
+    double* pan = matP + DP * LDM;             // [DP][LDP]  panel: row k = reduction index, column = frame
+    __shared__ int s_m, s_first, s_n;
+    const int D2 = p.D2;
+    if (threadIdx.x == 0) {
+        const int tile = blockIdx.x;
+        int lo = 0, hi = p.M;                  // largest m with tstart[m] <= tile
+        while (hi - lo > 1) { const int mid_m = (lo + hi) >> 1; if (p.tstart[mid_m] <= tile) lo = mid_m; else hi = mid_m; }
+        const bool live = tile < p.tstart[p.M];
+        const int first = p.mstart[lo] + (tile - p.tstart[lo]) * kFT;
+        s_m = lo; s_first = first; s_n = live ? min(kFT, p.mstart[lo + 1] - first) : 0;
+    }
+    __syncthreads();
+    const int m = s_m, nf = s_n;
+    if (nf <= 0) return;
+    const int32_t* frames = p.perm + s_first;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, r = lane >> 2, q = lane & 3;
+
+    // ---- matrices: cp.async when every column is a whole number of 16-byte pieces, plain loads otherwise
+    auto stage = [&](double* dst, const double* src) {
+        const double* sm_ = src + (size_t)m * D2 * D2;
+        if ((D2 & 1) == 0) {
+            const int pieces = D2 / 2;
+            for (int e = tid; e < D2 * pieces; e += 256) {
+                const int k = e / pieces, i2 = e - k * pieces;
+                cp_async16_g(dst + (size_t)k * LDM + 2 * i2, sm_ + (size_t)k * D2 + 2 * i2);
+            }
+        } else {
+            for (int e = tid; e < D2 * D2; e += 256) {
+                const int k = e / D2, i = e - k * D2;
+                dst[(size_t)k * LDM + i] = sm_[e];
+            }
+        }
+        // zero the padding rows / columns the fragments touch
+        for (int e = tid; e < DP * (DP - D2); e += 256) {
+            const int k = e / (DP - D2), i = D2 + e - k * (DP - D2);
+            dst[(size_t)k * LDM + i] = 0.0;
+        }
+        for (int e = tid; e < (DP - D2) * LDM; e += 256) dst[(size_t)D2 * LDM + e] = 0.0;
+    };
+    if (MODE == 0) stage(matA, p.A);
+    stage(matP, p.P);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    // ---- panel: every warp gathers its own 8 frames (lane: frame c = lane/4, reduction indices k = q, q+4, ..)
+    {
+        const int f = 8 * w + r;
+        const bool live = f < nf;
+        const int64_t t = live ? frames[f] : 0;
+        for (int k = q; k < DP; k += 4) {
+            double v = 0.0;
+            if (live && k < D2) {
+                if (MODE == 0) {
+                    v = p.X[t * p.ldx + k] - p.mux[(size_t)m * D2 + k];
+                } else {
+                    const int Ds = D2 >> 1;
+                    double wy;
+                    if (k < Ds) {
+                        wy = p.Y[t * p.ldy + k];
+                    } else {
+                        const unsigned char ed = p.edge[t];
+                        wy = 0.0;
+                        if (!(ed & 1)) wy = -0.5 * p.Y[(t - 1) * p.ldy + k - Ds];
+                        if (!(ed & 2)) wy = fma(0.5, p.Y[(t + 1) * p.ldy + k - Ds], wy);
+                    }
+                    v = p.E[t * D2 + k] - wy;
+                }
+            }
+            pan[(size_t)k * LDP + f] = v;
+        }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+
+    // C[8i + r][8w + 2q + {0,1}] += sum_k Mat[8i + r][k] * Pan[k][8w + ..]:  a = Mat[8i + r][k0 + q],  b = Pan[k0 + q][8w + r]
+    auto product = [&](const double* mat, double2 (&acc)[NI]) {
+        const double* ap = mat + (size_t)q * LDM + r;
+        const double* bp = pan + (size_t)q * LDP + 8 * w + r;
+#pragma unroll 2
+        for (int k0 = 0; k0 < DP; k0 += 4) {
+            const double b = bp[(size_t)k0 * LDP];
+#pragma unroll
+            for (int i = 0; i < NI; ++i) dmma_acc(acc[i], ap[(size_t)k0 * LDM + 8 * i], b);
+        }
+    };
+    const int f0 = 8 * w + 2 * q;
+    const int64_t t0 = (f0 < nf) ? frames[f0] : -1, t1 = (f0 + 1 < nf) ? frames[f0 + 1] : -1;
+    double2 acc[NI];
+    if (MODE == 0) {
+        // ---- E = muy + A panel
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const double b = (8 * i + r < D2) ? p.muy[(size_t)m * D2 + 8 * i + r] : 0.0;
+            acc[i] = make_double2(b, b);
+        }
+        product(matA, acc);
+        __syncwarp();            // every lane of the warp has read the x - mux columns of its frames
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const int row = 8 * i + r;
+            *reinterpret_cast<double2*>(pan + (size_t)row * LDP + f0) = acc[i];      // the E panel of this warp's frames
+            if (row < D2) {
+                if (t0 >= 0) { p.E[t0 * D2 + row] = acc[i].x; if (p.Eout) p.Eout[t0 * D2 + row] = acc[i].x; }
+                if (t1 >= 0) { p.E[t1 * D2 + row] = acc[i].y; if (p.Eout) p.Eout[t1 * D2 + row] = acc[i].y; }
+            }
+        }
+        __syncwarp();
+    }
+    // ---- G = P (E panel | GV panel)
+#pragma unroll
+    for (int i = 0; i < NI; ++i) acc[i] = make_double2(0.0, 0.0);
+    product(matP, acc);
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        const int row = 8 * i + r;
+        if (row < D2) {
+            if (t0 >= 0) p.G[t0 * D2 + row] = acc[i].x;
+            if (t1 >= 0) p.G[t1 * D2 + row] = acc[i].y;
+        }
+    }
+}
+
+template <int MODE>
+static int32_t launch_group_dmma(const GroupParams& p, int64_t npanels, cudaStream_t st) {
+    const int NI = (p.D2 + 7) / 8, DP = 8 * NI;
+    const size_t smem = ((size_t)(MODE == 0 ? 2 : 1) * DP * (DP + 8) + (size_t)DP * (kFT + 8)) * sizeof(double);
+#define VCB_GROUP_CASE(N)                                                                                             \
+    case N:                                                                                                           \
+        VCB_CUDA(cudaFuncSetAttribute(group_panel_dmma_kernel<MODE, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        group_panel_dmma_kernel<MODE, N><<<(unsigned)npanels, 256, smem, st>>>(p);                                    \
+        break;
+    switch (NI) {
+        VCB_GROUP_CASE(1) VCB_GROUP_CASE(2) VCB_GROUP_CASE(3) VCB_GROUP_CASE(4) VCB_GROUP_CASE(5) VCB_GROUP_CASE(6)
+        VCB_GROUP_CASE(7) VCB_GROUP_CASE(8) VCB_GROUP_CASE(9) VCB_GROUP_CASE(10) VCB_GROUP_CASE(11) VCB_GROUP_CASE(12)
+        default: return fail(VCB_EUNSUPPORTED, "grouped DMMA product covers dimensions <= 96 (got %d)", p.D2);
+    }
+#undef VCB_GROUP_CASE
+    count_launch();
+    VCB_CUDA(cudaGetLastError());
+    return VCB_OK;
+}
+
 // ---- exact arg-max for the frames flagged as near ties, as panels -------------------------------
 // The flagged frames (a few per thousand) need c_m - 1/2 |Linv_m (x - mux_m)|^2 in Float64 for EVERY
 // mixture.  A block per frame streamed 64 x 18 KB of Linv from L2 per frame (L2-bandwidth bound,
@@ -345,6 +511,9 @@ static int32_t launch_group(int mode, GroupParams& p, const int* ws, int M, int6
     p.tstart = ws + 2 * (M + 1);
     p.perm = ws + 4 * (M + 1);
     p.M = M;
+    // FP64 tensor-core panels for D2 <= 96 (VCB_GROUP=simt keeps the register-tiled DFMA kernel)
+    static const bool simt = [] { const char* e = getenv("VCB_GROUP"); return e && e[0] == 's'; }();
+    if (p.D2 <= 96 && !simt) return mode == 0 ? launch_group_dmma<0>(p, npanels, st) : launch_group_dmma<1>(p, npanels, st);
     const int D2p = (p.D2 + 3) & ~3, TI = D2p / 4;
     const int threads = std::min(1024, round_up(TI * (kFT / 4), 32));
     if (TI * (kFT / 4) > 1024) return fail(VCB_EUNSUPPORTED, "feature dimension %d too large for the grouped product", p.D2);

@@ -289,6 +289,7 @@ end
 
 function fvpostf!(vs::VarianceScaling, src::Matrix{Float64})
     D, T = size(src)
+    length(vs.σ²) == D || throw(DimensionMismatch("VarianceScaling has $(length(vs.σ²)) entries, src has $D rows"))
     check(ccall((:vcb_variance_scaling_batch, libvcb200), Int32,
                 (Ptr{Float64}, Int32, Ptr{Float64}, Int64, Ptr{Int64}, Int64, Ptr{Float64}, Int64),
                 vs.σ², D, src, D, Int64[0, T], 1, src, D))
