@@ -62,14 +62,14 @@ template <int BITS, int TT, int MAXT, int MINB, int DT, int BS, int FS, int SPT>
 __global__ void __launch_bounds__(MAXT, MINB)
 dtw_fused_kernel(const double* __restrict__ tmplT, const int64_t* __restrict__ toff,
                  const double* __restrict__ seq, const int64_t* __restrict__ soff,
-                 const int64_t* __restrict__ bpoff, uint32_t* __restrict__ bp, int Drt, int fstep_rt,
-                 int bstep_rt, int64_t* __restrict__ paths, double* __restrict__ final_cost) {
+                 const int64_t* __restrict__ bpoff, const int64_t* __restrict__ order, uint32_t* __restrict__ bp,
+                 int Drt, int fstep_rt, int bstep_rt, int64_t* __restrict__ paths, double* __restrict__ final_cost) {
     constexpr int PER = 32 / BITS;
     constexpr uint32_t MASK = (BITS == 32) ? 0xFFFFFFFFu : ((1u << BITS) - 1u);
     static_assert(TT % 2 == 0, "sequence tiles are read as double2");
     const int D = DT > 0 ? DT : Drt;
     const int bstep = BS >= 0 ? BS : bstep_rt, fstep = BS >= 0 ? FS : fstep_rt;
-    const int p = blockIdx.x;
+    const int p = (int)order[blockIdx.x];      // pairs are launched by decreasing cost (the long ones first)
     const int64_t tb = toff[p], sb = soff[p];
     const int S = (int)(toff[p + 1] - tb);
     const int T = (int)(soff[p + 1] - sb);
@@ -270,7 +270,7 @@ dtw_fused_kernel(const double* __restrict__ tmplT, const int64_t* __restrict__ t
 
 template <int BITS, int TT, int MAXT, int MINB, int DT, int BS, int FS, int SPT>
 static int32_t launch_dtw_cfg(const double* tmplT, const int64_t* d_toff, const double* seq,
-                              const int64_t* d_soff, const int64_t* d_bpoff, uint32_t* bp, int D,
+                              const int64_t* d_soff, const int64_t* d_bpoff, const int64_t* d_order, uint32_t* bp, int D,
                               int fstep, int bstep, int64_t npairs, int maxS, int64_t* paths,
                               double* final_cost, cudaStream_t st) {
     const int nt = round_up((maxS + SPT - 1) / SPT, 32);
@@ -278,7 +278,7 @@ static int32_t launch_dtw_cfg(const double* tmplT, const int64_t* d_toff, const 
     const size_t smem = (size_t)(2 * colw + D * TT) * sizeof(double);
     auto k = dtw_fused_kernel<BITS, TT, MAXT, MINB, DT, BS, FS, SPT>;
     VCB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<(unsigned)npairs, nt, smem, st>>>(tmplT, d_toff, seq, d_soff, d_bpoff, bp, D, fstep, bstep, paths, final_cost);
+    k<<<(unsigned)npairs, nt, smem, st>>>(tmplT, d_toff, seq, d_soff, d_bpoff, d_order, bp, D, fstep, bstep, paths, final_cost);
     count_launch();
     VCB_CUDA(cudaGetLastError());
     return VCB_OK;
@@ -308,13 +308,13 @@ __device__ __forceinline__ void st_release_shared(volatile int* p, int v) {
 template <int BITS, int TT, int REGS, int DT, int BS>
 __global__ void __maxnreg__(REGS)
 dtw_pipe_kernel(const double* __restrict__ tmplT, const int64_t* __restrict__ toff, const double* __restrict__ seq,
-                const int64_t* __restrict__ soff, const int64_t* __restrict__ bpoff, uint32_t* __restrict__ bp,
-                int64_t* __restrict__ paths, double* __restrict__ final_cost) {
+                const int64_t* __restrict__ soff, const int64_t* __restrict__ bpoff, const int64_t* __restrict__ order,
+                uint32_t* __restrict__ bp, int64_t* __restrict__ paths, double* __restrict__ final_cost) {
     constexpr int PER = 32 / BITS, R = 32;       // R: ring slots (columns a warp may run ahead of its consumer)
     constexpr uint32_t MASK = (1u << BITS) - 1u;
     static_assert(DT % 2 == 0 && (BS == 1 || BS == 2), "pipeline kernel: even dimension, bstep 1 or 2, fstep 0");
     constexpr int D = DT;
-    const int p = blockIdx.x;
+    const int p = (int)order[blockIdx.x];
     const int64_t tb = toff[p], sb = soff[p];
     const int S = (int)(toff[p + 1] - tb);
     const int T = (int)(soff[p + 1] - sb);
@@ -507,13 +507,13 @@ dtw_pipe_kernel(const double* __restrict__ tmplT, const int64_t* __restrict__ to
 
 template <int BITS, int TT, int REGS, int DT, int BS>
 static int32_t launch_dtw_pipe(const double* tmplT, const int64_t* d_toff, const double* seq, const int64_t* d_soff,
-                               const int64_t* d_bpoff, uint32_t* bp, int64_t npairs, int maxS, int64_t* paths,
+                               const int64_t* d_bpoff, const int64_t* d_order, uint32_t* bp, int64_t npairs, int maxS, int64_t* paths,
                                double* final_cost, cudaStream_t st) {
     const int nt = round_up(maxS, 32), nw = nt / 32;
     const size_t smem = ((size_t)nw * 32 * 2 + nt + (size_t)nw * 2 * TT * DT) * sizeof(double) + (size_t)nw * sizeof(int);
     auto k = dtw_pipe_kernel<BITS, TT, REGS, DT, BS>;
     VCB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<(unsigned)npairs, nt, smem, st>>>(tmplT, d_toff, seq, d_soff, d_bpoff, bp, paths, final_cost);
+    k<<<(unsigned)npairs, nt, smem, st>>>(tmplT, d_toff, seq, d_soff, d_bpoff, d_order, bp, paths, final_cost);
     count_launch();
     VCB_CUDA(cudaGetLastError());
     return VCB_OK;
@@ -521,10 +521,10 @@ static int32_t launch_dtw_pipe(const double* tmplT, const int64_t* d_toff, const
 
 template <int BITS, int DT, int BS, int FS>
 static int32_t launch_dtw(const double* tmplT, const int64_t* d_toff, const double* seq,
-                          const int64_t* d_soff, const int64_t* d_bpoff, uint32_t* bp, int D,
+                          const int64_t* d_soff, const int64_t* d_bpoff, const int64_t* d_order, uint32_t* bp, int D,
                           int fstep, int bstep, int64_t npairs, int maxS, int64_t* paths,
                           double* final_cost, cudaStream_t st) {
-#define VCB_DTW_ARGS tmplT, d_toff, seq, d_soff, d_bpoff, bp, D, fstep, bstep, npairs, maxS, paths, final_cost, st
+#define VCB_DTW_ARGS tmplT, d_toff, seq, d_soff, d_bpoff, d_order, bp, D, fstep, bstep, npairs, maxS, paths, final_cost, st
     const int nt = round_up(maxS, 32);
     static const int two_ctas = [] { const char* e = getenv("VCB_DTW_2CTA"); return e ? atoi(e) : 1; }();
     // VCB_DTW_PIPE=1: barrier-free warp pipeline for the reference's own windows (fstep 0, bstep 1 / 2) and
@@ -534,8 +534,8 @@ static int32_t launch_dtw(const double* tmplT, const int64_t* d_toff, const doub
     // warps of a CTA still move through observation and recurrence phases together.  Kept as an experiment.
     static const int pipe = [] { const char* e = getenv("VCB_DTW_PIPE"); return e ? atoi(e) : 0; }();
     if constexpr (DT > 0 && DT % 2 == 0 && FS == 0 && (BS == 1 || BS == 2) && BITS == 2) {
-        if (pipe && nt <= 672) return launch_dtw_pipe<BITS, 8, 48, DT, BS>(tmplT, d_toff, seq, d_soff, d_bpoff, bp, npairs, maxS, paths, final_cost, st);
-        if (pipe && nt <= 1024) return launch_dtw_pipe<BITS, 8, 64, DT, BS>(tmplT, d_toff, seq, d_soff, d_bpoff, bp, npairs, maxS, paths, final_cost, st);
+        if (pipe && nt <= 672) return launch_dtw_pipe<BITS, 8, 48, DT, BS>(tmplT, d_toff, seq, d_soff, d_bpoff, d_order, bp, npairs, maxS, paths, final_cost, st);
+        if (pipe && nt <= 1024) return launch_dtw_pipe<BITS, 8, 64, DT, BS>(tmplT, d_toff, seq, d_soff, d_bpoff, d_order, bp, npairs, maxS, paths, final_cost, st);
     }
     // <= 672 states and a compile-time dimension: two CTAs per SM (8-column tiles, 48 registers): one
     // CTA's barrier-paced recurrence overlaps the other's FP64-bound observation costs (the
@@ -568,10 +568,10 @@ static int32_t launch_dtw(const double* tmplT, const int64_t* d_toff, const doub
 // both fstep=0) and common mel-cepstrum orders; everything else takes the runtime-parameter build.
 template <int BITS, int BS, int FS>
 static int32_t launch_dtw_dim(const double* tmplT, const int64_t* d_toff, const double* seq,
-                              const int64_t* d_soff, const int64_t* d_bpoff, uint32_t* bp, int D,
+                              const int64_t* d_soff, const int64_t* d_bpoff, const int64_t* d_order, uint32_t* bp, int D,
                               int fstep, int bstep, int64_t npairs, int maxS, int64_t* paths,
                               double* final_cost, cudaStream_t st) {
-#define VCB_DTW_ARGS tmplT, d_toff, seq, d_soff, d_bpoff, bp, D, fstep, bstep, npairs, maxS, paths, final_cost, st
+#define VCB_DTW_ARGS tmplT, d_toff, seq, d_soff, d_bpoff, d_order, bp, D, fstep, bstep, npairs, maxS, paths, final_cost, st
     if constexpr (BS >= 0) {
         switch (D) {
             case 24: return launch_dtw<BITS, 24, BS, FS>(VCB_DTW_ARGS);
@@ -602,13 +602,19 @@ int32_t dtw_fit_batch_device(const double* d_tmpl, const int64_t* h_toff, const 
         maxS = (int)std::max<int64_t>(maxS, S);
         bpoff[p + 1] = bpoff[p] + ((T + per - 1) / per) * ((S + 31) / 32 * 32);
     }
+    // launch order: decreasing cost S*T, so the short pairs fill the tail of the last wave
+    std::vector<int64_t> order(npairs);
+    for (int64_t p = 0; p < npairs; ++p) order[p] = p;
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+        return (h_toff[a + 1] - h_toff[a]) * (h_soff[a + 1] - h_soff[a]) > (h_toff[b + 1] - h_toff[b]) * (h_soff[b + 1] - h_soff[b]);
+    });
     const int64_t totalS = h_toff[npairs];
     // scratch: offsets, transposed templates, packed back-pointers (stream-ordered allocation)
     int64_t* d_off = nullptr;
     double* d_tmplT = nullptr;
     uint32_t* d_bp = nullptr;
     const size_t noff = (size_t)(npairs + 1);
-    VCB_CUDA(cudaMallocAsync((void**)&d_off, 3 * noff * sizeof(int64_t), st));
+    VCB_CUDA(cudaMallocAsync((void**)&d_off, 4 * noff * sizeof(int64_t), st));
     VCB_CUDA(cudaMallocAsync((void**)&d_tmplT, (size_t)totalS * D * sizeof(double), st));
     VCB_CUDA(cudaMallocAsync((void**)&d_bp, (size_t)std::max<int64_t>(bpoff[npairs], 1) * sizeof(uint32_t), st));
     // offsets are tiny; pageable async copies complete before return of the call for the host
@@ -616,6 +622,7 @@ int32_t dtw_fit_batch_device(const double* d_tmpl, const int64_t* h_toff, const 
     VCB_CUDA(cudaMemcpyAsync(d_off, h_toff, noff * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     VCB_CUDA(cudaMemcpyAsync(d_off + noff, h_soff, noff * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     VCB_CUDA(cudaMemcpyAsync(d_off + 2 * noff, bpoff.data(), noff * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    VCB_CUDA(cudaMemcpyAsync(d_off + 3 * noff, order.data(), (size_t)npairs * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     stage_begin(st);
     {
         dim3 grid((unsigned)npairs, (maxS + 31) / 32), block(32, 8);
@@ -625,7 +632,7 @@ int32_t dtw_fit_batch_device(const double* d_tmpl, const int64_t* h_toff, const 
     }
     stage_mark(st);      // [0] template transpose; [1] the fused kernel
     int32_t rc;
-#define VCB_DTW_CALL d_tmplT, d_off, d_seq, d_off + noff, d_off + 2 * noff, d_bp, D, fstep, bstep, npairs, maxS, d_paths, d_final_cost, st
+#define VCB_DTW_CALL d_tmplT, d_off, d_seq, d_off + noff, d_off + 2 * noff, d_off + 3 * noff, d_bp, D, fstep, bstep, npairs, maxS, d_paths, d_final_cost, st
     if (fstep == 0 && bstep == 1) rc = launch_dtw_dim<2, 1, 0>(VCB_DTW_CALL);
     else if (fstep == 0 && bstep == 2) rc = launch_dtw_dim<2, 2, 0>(VCB_DTW_CALL);
     else if (bits == 2) rc = launch_dtw_dim<2, -1, 0>(VCB_DTW_CALL);
