@@ -450,8 +450,7 @@ def run_fbf(ctx: Ctx, steps: int, warmup: int) -> dict:
     used_tc = args.variant != 1
     prof = ncu_summary("prof_fbf_tc" if used_tc else "prof_fbf_simt")
     cfg = config_for("fbf", ctx.world)
-    cfg["frames_per_gpu"] = T
-    cfg["kernel"] = "tcgen05 3xTF32 (gmm_tc_kernel)" if used_tc else "CUDA-core fp32 (gmm_simt_kernel)"
+    cfg["frames_per_gpu"] = T        # (identical to the --impl reference arm's config unless --frames is given)
     return {
         "metric": METRICS["fbf"], "value": value, "unit": "frames/s", "n_gpus": ctx.world, "steps": steps,
         "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -156,7 +156,7 @@ struct WarpLayout {
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     const unsigned a = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(a), "l"(gmem) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(32, MINB) traj_solve_warp(const TrajParams p) 
             }
 #pragma unroll
             for (int e = 0; e < NF; ++e) {
-                F[(NL + e) * 32] = G1[e];     // L[t][t-2] is not stored: the back substitution rebuilds its
+                __stcs(&F[(NL + e) * 32], G1[e]);      // streamed: 3.7 GB of factors pass through once     // L[t][t-2] is not stored: the back substitution rebuilds its
                                               // product from P (L2-resident) and Linv_{t-2}
                 sLp[e][lane] = G1[e];       // all reads of the old L[t-1][t-2] are complete (warp-synchronous)
             }
@@ -665,7 +665,7 @@ __global__ void __launch_bounds__(32, MINB) traj_solve_warp(const TrajParams p) 
             }
 #pragma unroll
             for (int e = 0; e < NL; ++e) {
-                F[e * 32] = Li[e];
+                __stcs(&F[e * 32], Li[e]);
                 LinvT[e][lane] = Li[e];
             }
         }
@@ -916,7 +916,7 @@ __global__ void __maxnreg__(128) traj_solve_pair(const TrajParams p) {
             }
 #pragma unroll
             for (int e = 0; e < NL; ++e) {
-                F[e * 32] = Li[e];
+                __stcs(&F[e * 32], Li[e]);
                 slot[e][lane] = Li[e];
             }
             __threadfence_block();
@@ -1101,7 +1101,7 @@ __global__ void __maxnreg__(128) traj_solve_pair(const TrajParams p) {
         //      L[t][t-1] of the next step; request the R[t+1][t+1] tiles
 #pragma unroll
         for (int e = 0; e < NF; ++e) {
-            F[(NL + e) * 32] = G1[e];
+            __stcs(&F[(NL + e) * 32], G1[e]);      // streamed: 3.7 GB of factors pass through once
             sLp[e][lane] = G1[e];
         }
         mprev = m0; m0 = m1; m1 = m2; m2 = m3;
