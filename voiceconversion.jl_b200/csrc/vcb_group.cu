@@ -310,12 +310,22 @@ __global__ void __launch_bounds__(256) group_panel_dmma_kernel(const GroupParams
         const int f = 8 * w + r;
         const bool live = f < nf;
         const int64_t t = live ? frames[f] : 0;
-        for (int k = q; k < DP; k += 4) {
-            double v = 0.0;
-            if (live && k < D2) {
-                if (MODE == 0) {
-                    v = p.X[t * p.ldx + k] - p.mux[(size_t)m * D2 + k];
-                } else {
+        if (MODE == 0) {
+            // all loads of the lane first (2 NI independent requests in flight), then the subtractions
+            double xv[2 * NI], mv[2 * NI];
+#pragma unroll
+            for (int j = 0; j < 2 * NI; ++j) {
+                const int k = q + 4 * j;
+                const bool ok = live && k < D2;
+                xv[j] = ok ? p.X[t * p.ldx + k] : 0.0;
+                mv[j] = ok ? p.mux[(size_t)m * D2 + k] : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 2 * NI; ++j) pan[(size_t)(q + 4 * j) * LDP + f] = xv[j] - mv[j];
+        } else {
+            for (int k = q; k < DP; k += 4) {
+                double v = 0.0;
+                if (live && k < D2) {
                     const int Ds = D2 >> 1;
                     double wy;
                     if (k < Ds) {
@@ -328,8 +338,8 @@ __global__ void __launch_bounds__(256) group_panel_dmma_kernel(const GroupParams
                     }
                     v = p.E[t * D2 + k] - wy;
                 }
+                pan[(size_t)k * LDP + f] = v;
             }
-            pan[(size_t)k * LDP + f] = v;
         }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
