@@ -86,3 +86,21 @@ def test_multi_device_mode_matches_single_device(vcb, oracle):
         assert np.array_equal(pmulti, ref)
     finally:
         vcb.init(1)
+
+
+def test_pinned_arrays(vcb):
+    """pinned_empty returns page-locked column-major arrays (vcb_host_alloc); the host paths accept them
+    as inputs and result buffers and free them with their last view."""
+    import gc
+    gm, fm = vcb.synth.config_c1(5000)
+    g = vcb.GMMMap(*gm)
+    a = vcb.pinned_empty(fm.shape)
+    assert a.flags.f_contiguous and a.dtype == np.float64
+    a[...] = fm
+    out = vcb.pinned_empty(fm.shape)
+    vcb.vc(g, a, out=out)
+    assert np.array_equal(out, vcb.vc(g, fm))
+    view = out[:, 10:20]
+    del out, a
+    gc.collect()
+    assert np.isfinite(view).all()

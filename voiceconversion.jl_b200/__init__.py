@@ -35,7 +35,7 @@ __all__ = [
     "fvconvert", "fvconvert_gv", "vc", "vc_batch", "vc_static_batch", "ncomponents", "dim", "predict_proba",
     "predict", "constructW", "push_delta", "align", "align_batch", "DTWs", "DimensionMismatch",
     "PosDefException", "SingularException", "ArgumentError", "CudaError", "VCBError",
-    "set_device", "device_count", "init", "set_kernel_variant", "launch_count", "traj_status",
+    "set_device", "device_count", "init", "set_kernel_variant", "launch_count", "traj_status", "pinned_empty",
 ]
 
 
@@ -239,6 +239,43 @@ class TrajectoryGVGMMMap(TrajectoryConverter):
 class VarianceScaling(NamedTuple):
     """``VarianceScaling(sigma2)``  (src/gv.jl:6-8)."""
     sigma2: np.ndarray
+
+
+class _PinnedBuffer:
+    """Owner of one vcb_host_alloc allocation (freed when the last array view dies)."""
+
+    def __init__(self, nbytes: int):
+        self.ptr = C.c_void_p()
+        _lib.check(_lib.lib().vcb_host_alloc(C.byref(self.ptr), max(int(nbytes), 1)))
+        self.nbytes = int(nbytes)
+
+    def __del__(self):
+        p = getattr(self, "ptr", None)
+        if p:
+            try:
+                _lib.lib().vcb_host_free(p)
+            except Exception:
+                pass
+            self.ptr = None
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """Column-major array in page-locked host memory (``vcb_host_alloc``): host<->device copies of such
+    arrays run at PCIe speed and keep the library's copy/compute pipelines asynchronous; ordinary
+    (pageable) arrays are staged by the driver at a fraction of that."""
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape))
+    owner = _PinnedBuffer(n * dt.itemsize)
+    buf = (C.c_char * (n * dt.itemsize)).from_address(owner.ptr.value)
+    a = np.frombuffer(buf, dtype=dt, count=n).reshape(shape, order="F")
+    a.flags.writeable = True
+    _PINNED_OWNERS[id(buf)] = owner           # keep the allocation alive as long as the ctypes buffer is
+    import weakref
+    weakref.finalize(buf, _PINNED_OWNERS.pop, id(buf), None)
+    return a
+
+
+_PINNED_OWNERS: dict = {}
 
 
 def traj_status(t: "TrajectoryGMMMap") -> None:

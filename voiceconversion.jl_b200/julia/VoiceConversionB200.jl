@@ -58,6 +58,20 @@ function init(ndev::Integer=0)
     Int(n[])
 end
 
+# Page-locked arrays: host<->device copies of ordinary (pageable) Julia arrays go through the driver's staging
+# buffers at a fraction of PCIe speed and serialise the library's copy/compute pipelines.  `pinned_matrix`
+# returns a Matrix{Float64} in page-locked memory (freed by its finalizer); `pin!` / `unpin!` page-lock a
+# long-lived array in place.
+function pinned_matrix(rows::Integer, cols::Integer)
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:vcb_host_alloc, libvcb200), Int32, (Ref{Ptr{Cvoid}}, Csize_t), p, rows * cols * sizeof(Float64)))
+    A = unsafe_wrap(Array, Ptr{Float64}(p[]), (Int(rows), Int(cols)); own=false)
+    finalizer(_ -> ccall((:vcb_host_free, libvcb200), Int32, (Ptr{Cvoid},), p[]), A)
+    A
+end
+pin!(A::Array{Float64}) = (check(ccall((:vcb_host_register, libvcb200), Int32, (Ptr{Cvoid}, Csize_t), A, sizeof(A))); A)
+unpin!(A::Array{Float64}) = (check(ccall((:vcb_host_unregister, libvcb200), Int32, (Ptr{Cvoid},), A)); A)
+
 # ---- type hierarchy (src/common.jl:2-4) -----------------------------------------------------------
 abstract type AbstractConverter end
 abstract type FrameByFrameConverter <: AbstractConverter end
