@@ -580,6 +580,12 @@ def run_traj(ctx: Ctx, steps: int, warmup: int, which: str = "c4", limit: int = 
                      "algorithmic_bytes_per_frame": B_TRAJ, "frames_per_launch": local_frames,
                      "step_frac": B_TRAJ * local_frames / (ms * 1e-3) / 1e9 / hbm,
                      "peak_source": f"HBM copy bandwidth {ctx.peak_src}",
+                     "fp64_pipe": {"pipe_cycles_per_frame": 240 * 16.1 + 900 * 2.2,
+                                   "floor_ms": (240 * 16.1 + 900 * 2.2) * local_frames / (4 * 148) / ((ctx.peaks.get("sm_max_mhz") or 1965.0) * 1e3),
+                                   "frac_of_floor": (240 * 16.1 + 900 * 2.2) * local_frames / (4 * 148) / ((ctx.peaks.get("sm_max_mhz") or 1965.0) * 1e3) / kms,
+                                   "ncu_pipe_active_pct": {"dmma": prof.get("sm__pipe_tensor_cycles_active"), "fp64": prof.get("sm__pipe_fp64_cycles_active")},
+                                   "note": "the real bound: DMMA (16.1 cycles per sub-partition) and DFMA (2.2) share the FP64 pipe "
+                                           "(tools/micro/dmma_bench.cu); ~240 DMMA + ~900 FP64 instructions per frame, 592 sub-partitions"},
                      "note": "achieved = 28,224 B/frame (SURVEY 8d: L written + read once, E read, y written) x frames of "
                              "one launch / the band solver's own duration (CUDA events around the kernel inside the timed "
                              "region); step_frac divides by the whole step (arg-max + E/PE + solver) instead. The solver "
