@@ -827,7 +827,6 @@ __global__ void __launch_bounds__(32, MINB) traj_solve_warp(const TrajParams p) 
 // mix of product and factorisation warps.  Warp G runs the back substitution alone.
 // ------------------------------------------------------------------------------------------------
 constexpr int kBarG2C = 1, kBarC2G = 2;
-__device__ __forceinline__ unsigned __smid() { unsigned v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
 __device__ __forceinline__ void bar_sync64(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void bar_arrive64(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 
@@ -874,12 +873,11 @@ __global__ void __maxnreg__(128) traj_solve_pair(const TrajParams p) {
     // G warp on sub-partitions 0, 2, 1, 3
     const int pair_id = min(s_slot[0], s_slot[1]) >> 1;
     bool is_g = (wib == 0) == ((pair_id & 2) == 0);
+    // VCB_TRAJ_ROLE: other assignments, kept to reproduce the measurement (1/2: fixed, 3: by CTA parity, 4: by pair parity)
     if (p.role_rule == 1) is_g = wib == 0;
     if (p.role_rule == 2) is_g = wib == 1;
     if (p.role_rule == 3) is_g = (wib == 0) == ((blockIdx.x & 1) == 0);
     if (p.role_rule == 4) is_g = (wib == 0) == ((pair_id & 1) == 0);
-    if (p.role_rule == 5) is_g = (s_slot[wib] & 3) == (((pair_id >> 1) & 1) ? (max(s_slot[0], s_slot[1]) & 3) : (min(s_slot[0], s_slot[1]) & 3));
-    if (p.role_rule == 9 && blockIdx.x < 16 && lane == 0) printf("cta %d warp %d slot %d smid %d\n", blockIdx.x, wib, s_slot[wib], (int)__smid());
 
     if (!is_g) {
         // =========================== warp C: factorisation ===========================================
