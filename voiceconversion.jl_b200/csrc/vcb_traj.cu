@@ -525,7 +525,7 @@ int32_t traj_solve_device(const vcb_traj& tr, const double* dX, int64_t ldx, con
         TrajParams p{};
         p.P = tr.d_P.p; p.mhat = d_mhat; p.Gv = dG; p.chunk_off = d_chunk_off; p.Lst = dL; p.Z = dZ;
         p.Y = dY; p.ldy = ldy; p.Xpow = dX; p.ldx = ldx; p.copy_power = copy_power ? 1 : 0;
-        p.Ds = Ds; p.err = derr;
+        p.Ds = Ds; p.err = derr; p.nchunks = nchunks;
         if (warp_bytes) rc = traj_warp_launch(p, nchunks, st);
         else switch ((Ds + 7) / 8) {
             case 1: rc = launch_tiled<1>(p, nchunks, st); break;

@@ -17,6 +17,7 @@ struct TrajParams {
     int Ds;
     int* err;
     int role_rule;          // experiment switch of the two-warp solver (0 = default)
+    int64_t nchunks;
 };
 
 // Warp-per-chunk solver (vcb_traj_warp.cu): Ds <= 24.  Bytes of factor scratch per frame, 0 if the

@@ -375,15 +375,33 @@ __device__ __forceinline__ void back_sweep_ring(const TrajParams& p, double2 (*c
 // FULL: Ds == 8 NT (no padding, every 16-byte piece aligned): the 39 P tiles a step assembles its
 // R blocks from are prefetched into shared memory with cp.async during the previous step -- one
 // piece per lane and tile, read back only by the lane that requested it.
-template <int NT, bool FULL, int MINB = 1, bool COOP = false>
-__global__ void __launch_bounds__(32, MINB) traj_solve_warp(const TrajParams p) {
+// WPC (warps = chunks per CTA): 1, or 7 with PHASE-LOCKED warp pairs.  DMMA and DFMA share the FP64 pipe of an SM
+// sub-partition (tools/micro/dmma_bench.cu), and with seven one-warp CTAs per SM three sub-partitions carry two
+// unrelated warps whose product phases (a DMMA stream that saturates the pipe) and factorisation phases (a
+// latency-bound DFMA chain) meet at random: both in the chain, the pipe idles.  With WPC = 7 the SM holds ONE CTA;
+// warps w and w + 4 sit on the same sub-partition (hardware warp slots are handed out in order) and exchange one
+// named barrier per half step, so that one of them is always in its product phase while the other factorises.
+template <int NT, bool FULL, int MINB = 1, bool COOP = false, int WPC = 1>
+__global__ void __launch_bounds__(32 * WPC, WPC == 1 ? MINB : 1) traj_solve_warp(const TrajParams p) {
     using LY = WarpLayout<NT>;
     constexpr int DSP = LY::DSP, NL = LY::NL, NF = LY::NF, FT = LY::FT;
-    const int lane = threadIdx.x, r = lane >> 2, q = lane & 3;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, r = lane >> 2, q = lane & 3;
     const int Ds = p.Ds, D2 = 2 * Ds;
     const bool even = FULL || (Ds & 1) == 0;
-    const int64_t c0 = p.chunk_off[blockIdx.x];
-    const int T = (int)(p.chunk_off[blockIdx.x + 1] - c0);
+    const int64_t chunk = (int64_t)blockIdx.x * WPC + wib;
+    if (chunk >= p.nchunks) return;
+    const int64_t c0 = p.chunk_off[chunk];
+    const int T = (int)(p.chunk_off[chunk + 1] - c0);
+    // steps this warp walks in lock step with its partner on the same sub-partition (0: none)
+    int Tc = 0;
+    const bool is_b = wib >= 4;
+    if (WPC > 1) {
+        const int wp = wib ^ 4;
+        const int64_t cp = (int64_t)blockIdx.x * WPC + wp;
+        if (wp < WPC && cp < p.nchunks) Tc = min(T, (int)(p.chunk_off[cp + 1] - p.chunk_off[cp]));
+    }
+    const int pair_bar = 1 + (wib & 3);
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory"); };
     if (T <= 0) return;
 
     // one pool of 512-byte tiles: Linv_{t-1}, Linv_{t-2} (by parity of t) | L[t-1][t-2] | FULL: the P
@@ -391,15 +409,21 @@ __global__ void __launch_bounds__(32, MINB) traj_solve_warp(const TrajParams p) 
     // reuses the pool as a ring of factor tiles
     constexpr int NPT = 3 * NF + 2 * NL;
     constexpr int NPOOL = 2 * NL + NF + (FULL ? NPT : 0);
-    __shared__ __align__(16) double2 pool[NPOOL][32];
+    constexpr int kSmallDoubles = 64 + 3 * DSP + DSP + (FULL ? DSP : 2);      // sdiag | sz | sw | srow
+    constexpr size_t kWarpBytes = (size_t)NPOOL * 32 * sizeof(double2) + (size_t)((kSmallDoubles + 1) & ~1) * sizeof(double);
+    __shared__ __align__(16) double2 pool_s[WPC == 1 ? NPOOL : 1][32];
+    __shared__ __align__(16) double small_s[WPC == 1 ? kSmallDoubles : 2];
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    double2(*const pool)[32] = WPC == 1 ? pool_s : reinterpret_cast<double2(*)[32]>(dyn_smem + (size_t)wib * kWarpBytes);
+    double* const small = WPC == 1 ? small_s : reinterpret_cast<double*>(dyn_smem + (size_t)wib * kWarpBytes + (size_t)NPOOL * 32 * sizeof(double2));
     double2(*const sLinv0)[32] = pool;
     double2(*const sLp)[32] = pool + 2 * NL;
     double2(*const sP)[32] = pool + (FULL ? 2 * NL + NF : 0);
-    __shared__ __align__(16) double sdiag[64];
-    __shared__ __align__(16) double sz[3][DSP];
-    __shared__ __align__(16) double sw[DSP];
+    double* const sdiag = small;
+    double(*const sz)[DSP] = reinterpret_cast<double(*)[DSP]>(small + 64);
+    double* const sw = small + 64 + 3 * DSP;
     // FULL: r_t (the right-hand side row of the coming step), fetched by the same cp.async group as the P tiles
-    __shared__ __align__(16) double srow[FULL ? DSP : 2];
+    double* const srow = small + 64 + 4 * DSP;
 
     const int32_t* mh = p.mhat + c0;
     const double* gv = p.Gv + c0 * D2;
@@ -473,6 +497,7 @@ __global__ void __launch_bounds__(32, MINB) traj_solve_warp(const TrajParams p) 
         const double* const z2 = sz[(t + 1) % 3];
         double2* const F = Fb + (size_t)t * FT * 32;
         const int m3 = mh[t + 3 < T ? t + 3 : T - 1];     // consumed by the next step's prefetch
+        if (WPC > 1 && p.role_rule == 0 && is_b && t < Tc) pair_sync();       // anti-phase: B enters its product phase when A leaves its own
         double rr[NT];          // r_t = u_t + 1/2 v_{t-1} - 1/2 v_{t+1}, rows 8i + r
         if (!FULL) {
             const double wm = (t >= 1) ? 0.5 : 0.0, wp = (t + 1 < T) ? -0.5 : 0.0;
@@ -603,6 +628,7 @@ __global__ void __launch_bounds__(32, MINB) traj_solve_warp(const TrajParams p) 
                     }
                 }
         }
+        if (WPC > 1 && t < Tc) pair_sync();               // end of the product phase (A: lets B start; B: lets A start)
         // ---- 4b. w = r_t - G1 z_{t-1} - G2 z_{t-2};  stream G1, G2 out; G1 becomes L[t][t-1] of
         //          the next step
         {
@@ -671,6 +697,7 @@ __global__ void __launch_bounds__(32, MINB) traj_solve_warp(const TrajParams p) 
         }
         m0 = m1; m1 = m2; m2 = m3;
         __syncwarp();
+        if (WPC > 1 && (p.role_rule != 0 || !is_b) && t < Tc) pair_sync();      // end of the factorisation phase (anti-phase: A only; in-phase: both)
     }
 
     // =========================== backward: L' y = z ===========================================
@@ -1162,6 +1189,22 @@ int32_t launch_warp(const TrajParams& p, int64_t nchunks, cudaStream_t st) {
         }();
         (void)dbg;
         k<<<(unsigned)nchunks, 64, 0, st>>>(p2);
+        count_launch();
+        VCB_CUDA(cudaGetLastError());
+        return VCB_OK;
+    }
+    // VCB_TRAJ_WPC=7: one CTA of seven chunks per SM with phase-locked warp pairs (see traj_solve_warp)
+    static const int wpc = [] { const char* e = getenv("VCB_TRAJ_WPC"); return e ? atoi(e) : 1; }();
+    if (p.Ds == 8 * NT && wpc == 7) {
+        using LY = WarpLayout<NT>;
+        constexpr int NPOOL = 4 * LY::NL + 4 * LY::NF, kSmall = 64 + 5 * LY::DSP;
+        constexpr size_t kWarpBytes = (size_t)NPOOL * 512 + (size_t)((kSmall + 1) & ~1) * sizeof(double);
+        auto k = traj_solve_warp<NT, true, 1, false, 7>;
+        VCB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(7 * kWarpBytes)));
+        static const int phase = [] { const char* e = getenv("VCB_TRAJ_PHASE"); return e ? atoi(e) : 0; }();
+        TrajParams p3 = p;
+        p3.role_rule = phase;        // 0: partners in opposite phases, 1: partners in the same phase
+        k<<<(unsigned)((nchunks + 6) / 7), 224, 7 * kWarpBytes, st>>>(p3);
         count_launch();
         VCB_CUDA(cudaGetLastError());
         return VCB_OK;
