@@ -26,6 +26,11 @@ def _worker(rank, world, port, q):
         local_fm = np.asfortranarray(fm[:, off[b]:off[e]])
         local = O.vc_traj_batch(g, 6, local_fm, rel) if e > b else np.zeros((5, 0), order="F")
         gathered = vcb200.shard.gather_frames(torch.from_numpy(np.ascontiguousarray(local.T)), dist)
+        # the same gather with the shard sizes known up front (what bench.py --path traj does: no size exchange)
+        sizes = [int(off[vcb200.shard.shard_ragged(off, r, world)[0][1]] - off[vcb200.shard.shard_ragged(off, r, world)[0][0]])
+                 for r in range(world)]
+        again = vcb200.shard.gather_frames(torch.from_numpy(np.ascontiguousarray(local.T)), dist, sizes=sizes)
+        assert (again is None) == (rank != 0) and (rank != 0 or torch.equal(again, gathered))
         # frame-by-frame: contiguous frame ranges
         gm2 = vcb200.synth.random_joint_gmm(23, 3, 8)
         fm2 = vcb200.synth.fbf_feature_matrix(gm2, 101, 24)
