@@ -391,6 +391,22 @@ function backward(d::DTW)        # src/dtw.jl:133-145 (index chasing on the host
     end
     minpath
 end
+# batch of align(src, tgt) in ONE library call (the loop of bin/align.jl:84-113; sharded over the GPUs after init(0))
+function align(srcs::Vector{Matrix{Float64}}, tgts::Vector{Matrix{Float64}})
+    length(srcs) == length(tgts) || throw(ArgumentError("srcs and tgts must have the same length"))
+    D = size(srcs[1], 1)
+    all(m -> size(m, 1) == D, srcs) && all(m -> size(m, 1) == D, tgts) ||
+        throw(DimensionMismatch("order of feature vector must be equal"))
+    soff = Int64[0; cumsum(size.(srcs, 2))]
+    toff = Int64[0; cumsum(size.(tgts, 2))]
+    src, tgt = hcat(srcs...), hcat(tgts...)
+    newtgt = similar(src)
+    check(ccall((:vcb_align_batch, libvcb200), Int32,
+                (Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ptr{Int64}, Int64, Int32, Ptr{Float64}, Ptr{Int64}),
+                src, soff, tgt, toff, length(srcs), D, newtgt, C_NULL))
+    [(srcs[i], newtgt[:, soff[i]+1:soff[i+1]]) for i in 1:length(srcs)]
+end
+
 end # module DTWs
 using .DTWs
 
@@ -410,6 +426,22 @@ function align(src::Matrix{Float64}, tgt::Matrix{Float64})
                 (Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ptr{Int64}, Int64, Int32, Ptr{Float64}, Ptr{Int64}),
                 src, Int64[0, size(src, 2)], tgt, Int64[0, size(tgt, 2)], 1, size(src, 1), newtgt, C_NULL))
     src, newtgt
+end
+
+# batch of align(src, tgt) in ONE library call (the loop of bin/align.jl:84-113; sharded over the GPUs after init(0))
+function align(srcs::Vector{Matrix{Float64}}, tgts::Vector{Matrix{Float64}})
+    length(srcs) == length(tgts) || throw(ArgumentError("srcs and tgts must have the same length"))
+    D = size(srcs[1], 1)
+    all(m -> size(m, 1) == D, srcs) && all(m -> size(m, 1) == D, tgts) ||
+        throw(DimensionMismatch("order of feature vector must be equal"))
+    soff = Int64[0; cumsum(size.(srcs, 2))]
+    toff = Int64[0; cumsum(size.(tgts, 2))]
+    src, tgt = hcat(srcs...), hcat(tgts...)
+    newtgt = similar(src)
+    check(ccall((:vcb_align_batch, libvcb200), Int32,
+                (Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ptr{Int64}, Int64, Int32, Ptr{Float64}, Ptr{Int64}),
+                src, soff, tgt, toff, length(srcs), D, newtgt, C_NULL))
+    [(srcs[i], newtgt[:, soff[i]+1:soff[i+1]]) for i in 1:length(srcs)]
 end
 
 end # module
