@@ -46,6 +46,29 @@ def test_ragged_and_tiny(vcb, oracle):
         assert np.array_equal(paths, ref) and np.array_equal(fc, rfc)
 
 
+def test_ragged_and_tiny_compile_time_dimension(vcb, oracle):
+    """The same edge cases at D = 24 / 40, which take the compile-time-dimension kernels (the warp-pipeline
+    kernel hands tiles of 8 columns from warp to warp: sequences shorter than a tile, partial last tiles,
+    templates of less than a warp, exact multiples of 32 states and of 8 / 16 / 32 columns)."""
+    rng = np.random.default_rng(5)
+    S = [1, 2, 3, 31, 32, 33, 64, 65, 97, 672, 673, 1000, 1024]
+    T = [1, 9, 8, 7, 16, 31, 32, 33, 64, 100, 15, 37, 3]
+    to = np.concatenate([[0], np.cumsum(S)]); so = np.concatenate([[0], np.cumsum(T)])
+    for D in (24, 40):
+        tm = rng.standard_normal((D, to[-1])); sq = rng.standard_normal((D, so[-1]))
+        for fs, bs in [(0, 1), (0, 2)]:
+            paths, fc = vcb.DTWs.fit_batch(vcb.DTWs.DTW(fstep=fs, bstep=bs), tm, to, sq, so)
+            ref, rfc = oracle.dtw_fit_batch(tm, to, sq, so, fs, bs)
+            assert np.array_equal(paths, ref) and np.array_equal(fc, rfc), (D, fs, bs)
+        # short templates only: the CTA is a few warps wide (<= 672 threads takes the two-CTA build)
+        sel = [i for i in range(len(S)) if S[i] <= 97]
+        to2 = np.concatenate([[0], np.cumsum([S[i] for i in sel])]); so2 = np.concatenate([[0], np.cumsum([T[i] for i in sel])])
+        tm2 = np.concatenate([tm[:, to[i]:to[i + 1]] for i in sel], 1); sq2 = np.concatenate([sq[:, so[i]:so[i + 1]] for i in sel], 1)
+        paths, fc = vcb.DTWs.fit_batch(vcb.DTWs.DTW(fstep=0, bstep=2), tm2, to2, sq2, so2)
+        ref, rfc = oracle.dtw_fit_batch(tm2, to2, sq2, so2, 0, 2)
+        assert np.array_equal(paths, ref) and np.array_equal(fc, rfc), D
+
+
 @pytest.mark.parametrize("S,T", [(1025, 40), (1500, 300), (2500, 120), (4097, 33), (8192, 17)])
 def test_long_templates_bit_exact(vcb, oracle, S, T):
     """Templates beyond 1024 frames (5.1 s at the reference's 5 ms shift): the reference has no

@@ -21,6 +21,7 @@
 // The template is read through a k-major ("transposed") copy so the per-k loads are coalesced.
 #include <cstdlib>
 #include <type_traits>
+#include <utility>
 
 #include "vcb_kernels.h"
 
@@ -286,13 +287,18 @@ static int32_t launch_dtw_cfg(const double* tmplT, const int64_t* d_toff, const 
 
 // ------------------------------------------------------------------------------------------------
 // Barrier-free variant for the reference's own windows (fstep = 0, bstep = 1 or 2): dependencies then
-// run one way only, from lower to higher template states, so the warps of a CTA form a PIPELINE.
-// A thread keeps the cost of its state in a register; the two neighbours below come by shuffle, and
-// lanes 0/1 take them from a small shared-memory ring in which every warp publishes the costs of its
-// last two states per column together with a progress counter.  Warp w runs about one column behind
-// warp w-1 and never meets a CTA-wide barrier, so the FP64 pipe is never drained by one (the
-// per-column __syncthreads of dtw_fused_kernel was its largest stall).  The sequence frames of a tile
-// are read as warp-uniform (L1-resident) global loads.  Bit-exact with the same candidate order.
+// run one way only, from lower to higher template states, so the warps of a CTA form a PIPELINE whose
+// unit of hand-over is a TILE of TT columns.  A thread keeps the cost of its state in a register; inside
+// a tile the two neighbours below come by shuffle, and lanes 0/1 take them from a shared-memory ring in
+// which every warp publishes the costs of its last two states for each column of a tile, followed by ONE
+// release store of its progress counter per tile.  Warp w starts the recurrence of tile n when warp w-1
+// has finished it (one acquire poll per tile) and computes the observation costs of the tile -- the
+// FP64-bound part, which depends on nobody -- before it asks, so in the steady state the warps sit one
+// recurrence apart and the FP64 pipe always finds warps in their observation phase: there is no CTA-wide
+// barrier to drain it (the per-column __syncthreads of dtw_fused_kernel is its largest stall).
+// (Round 2's first version handed over every COLUMN: a release store, an acquire poll and a ring read
+// per column cost ~350 cycles against ~100 for a __syncthreads, 4.41 vs 2.79 ms; per tile the same
+// hand-over is amortised over TT columns.)  Bit-exact: same candidate order, same strict `<`.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int ld_acquire_shared(const volatile int* p) {
     int v;
@@ -305,14 +311,22 @@ __device__ __forceinline__ void st_release_shared(volatile int* p, int v) {
     asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 
+// f(integral_constant<int, 0>) ... f(integral_constant<int, N-1>): loop indices usable as asm immediates
+template <class F, int... I>
+__device__ __forceinline__ void static_for(F&& f, std::integer_sequence<int, I...>) { (f(std::integral_constant<int, I>{}), ...); }
+
 template <int BITS, int TT, int REGS, int DT, int BS>
 __global__ void __maxnreg__(REGS)
 dtw_pipe_kernel(const double* __restrict__ tmplT, const int64_t* __restrict__ toff, const double* __restrict__ seq,
                 const int64_t* __restrict__ soff, const int64_t* __restrict__ bpoff, const int64_t* __restrict__ order,
                 uint32_t* __restrict__ bp, int64_t* __restrict__ paths, double* __restrict__ final_cost) {
-    constexpr int PER = 32 / BITS, R = 32;       // R: ring slots (columns a warp may run ahead of its consumer)
+    constexpr int PER = 32 / BITS;
+    constexpr int RT = 4, R = RT * TT;           // ring: RT tiles of TT columns a warp may run ahead of its consumer
+    constexpr int RS = 4 * (R + 1);              // doubles per warp: positions 1..R of 4 doubles (position 0 unused)
+    constexpr int WPT = PER / TT;                // tiles per back-pointer word
     constexpr uint32_t MASK = (1u << BITS) - 1u;
-    static_assert(DT % 2 == 0 && (BS == 1 || BS == 2), "pipeline kernel: even dimension, bstep 1 or 2, fstep 0");
+    static_assert(DT % 4 == 0 && (BS == 1 || BS == 2), "pipeline kernel: dimension 4n, bstep 1 or 2, fstep 0");
+    static_assert(PER % TT == 0, "a back-pointer word is a whole number of tiles");
     constexpr int D = DT;
     const int p = (int)order[blockIdx.x];
     const int64_t tb = toff[p], sb = soff[p];
@@ -324,139 +338,138 @@ dtw_pipe_kernel(const double* __restrict__ tmplT, const int64_t* __restrict__ to
     uint32_t* bpp = bp + bpoff[p];
     const double kInf = __longlong_as_double(0x7FF0000000000000LL);
 
+    // ring[w][pos][4], pos = 1..R: the costs of the warp's last two states ENTERING column t sit at position
+    // ((t - 1) mod R) + 1 as [b1, b0, b1, b1] (b0: lane 30, b1: lane 31), so that lane 0 of the warp above reads
+    // (c1, c2) = (b1, b0) and lane 1 reads (-, c2) = (b1, b1) with one 16-byte load each, the positions a tile
+    // WRITES are contiguous (entering t0+1 .. t0+TT) and so are the ones it READS, except the first.
     extern __shared__ double smem[];
-    double* ring = smem;                                   // [nw][R][2]: costs of lanes 30, 31 after column t (slot t % R)
-    double* fin = smem + (size_t)nw * R * 2;               // [blockDim] final cost column
-    double* tiles = fin + blockDim.x;                      // [nw][2][TT][D] private double-buffered sequence tiles
-    volatile int* done = reinterpret_cast<volatile int*>(tiles + (size_t)nw * 2 * TT * D);   // [nw] latest published column
+    double* ring = smem;
+    double* fin = smem + (size_t)nw * RS;                  // [blockDim] final cost column
+    volatile int* done = reinterpret_cast<volatile int*>(fin + blockDim.x);   // [nw] columns published
     __shared__ double red_v[32];
     __shared__ int red_i[32];
     __shared__ int s_best;
 
     double c = active ? (double)(i + 1) : kInf;            // src/dtw.jl:49  costtable[:,1] = 1:S
-    if (lane >= 30) ring[((size_t)w * R + 0) * 2 + (lane - 30)] = c;
+    {
+        double* e0 = ring + (size_t)w * RS + 4 * R;        // entering column 0
+        if (lane == 30) e0[1] = c;
+        if (lane == 31) { e0[0] = c; e0[2] = c; e0[3] = c; }
+    }
     if (lane == 0) done[w] = (32 * w < S) ? 0 : 0x7FFFFFFF;     // warps without a state never hold anyone up
     __syncthreads();
     if (32 * w < S) {
         const double* tcol = tmplT + tb * D + i;           // element k at tcol[k * S]
-        const double* ring_prev = ring + (size_t)(w - 1) * R * 2;
-        double* ring_mine = ring + (size_t)w * R * 2;
+        // ring addresses as opaque 32-bit shared-memory offsets: one register each, immediate offsets per column
+        // (with generic pointers the compiler re-derives every address from scratch at this register budget)
+        unsigned rp32 = (unsigned)__cvta_generic_to_shared(ring + (size_t)(w > 0 ? w - 1 : 0) * RS + 2 * lane);    // lanes 0, 1 read
+        unsigned wp32 = (unsigned)__cvta_generic_to_shared(ring + (size_t)w * RS + (lane == 30 ? 1 : 0));
+        asm volatile("" : "+r"(rp32), "+r"(wp32));
         const bool last_warp = 32 * (w + 1) >= S;          // nobody consumes this warp's boundary
-        int avail = 0;                                     // columns of warp w-1 known to be published
-        int room = R - 1;                                  // columns this warp may still publish without asking
+        const bool rd = w > 0 && lane < 2;
+        const bool pub = !last_warp && lane >= 30, pub31 = !last_warp && lane == 31;
         uint32_t word = 0;
-        // the frames of a tile come through a private double buffer filled by cp.async one tile ahead (warps
-        // of the pipeline need a tile at different times, so there is no CTA-wide staging step)
-        double* const mytiles = tiles + (size_t)w * 2 * TT * D;
-        auto fetch_tile = [&](int t0n, int buf) {
-            if (t0n < T) {
-                const int pieces = min(TT, T - t0n) * (D / 2);
-                const double* src = seq + (sb + t0n) * D;
-                for (int e = lane; e < pieces; e += 32) {
-                    const unsigned a = (unsigned)__cvta_generic_to_shared(mytiles + (size_t)buf * TT * D + 2 * e);
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(a), "l"(src + 2 * e) : "memory");
-                }
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        fetch_tile(0, 0);
-        for (int t0 = 0, tile = 0; t0 < T; t0 += TT, ++tile) {
-            const int ncols = min(TT, T - t0);
-            fetch_tile(t0 + TT, (tile + 1) & 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-            __syncwarp();
+        const double* srow = seq + sb * D;                 // frames are read as warp-uniform (L1-resident) loads
+
+        auto tile_body = [&](auto full_tag, const int t0, const int tile) {
+            constexpr bool FULL = decltype(full_tag)::value;
+            const int ncols = FULL ? TT : T - t0;
+            const int tend = t0 + ncols;
             // ---- observation costs for TT frames: strict left-to-right Float64 sum, no FMA (src/dtw.jl:33-35)
             double acc[TT];
 #pragma unroll
             for (int cc = 0; cc < TT; ++cc) acc[cc] = 0.0;
             if (active) {
                 const double* tp = tcol;
-                const double2* vbase = reinterpret_cast<const double2*>(mytiles + (size_t)(tile & 1) * TT * D);
-#pragma unroll 2
-                for (int k2 = 0; k2 < D / 2; ++k2) {
-                    const double tk0 = tp[0], tk1 = tp[S];
-                    tp += 2 * S;
+                const double* vb = srow + (size_t)t0 * D;
+                int voff[TT];                              // partial tile: columns past the sequence re-read its last frame
+#pragma unroll
+                for (int cc = 0; cc < TT; ++cc) voff[cc] = (FULL ? cc : min(cc, ncols - 1)) * D;
+                // four dimensions of a frame per 32-byte load (sm_100: LDG.256; rows of D = 4n doubles keep the alignment)
+#pragma unroll 1
+                for (int k4 = 0; k4 < D; k4 += 4) {
+                    const double tk0 = tp[0], tk1 = tp[S], tk2 = tp[2 * (size_t)S], tk3 = tp[3 * (size_t)S];
+                    tp += 4 * (size_t)S;
 #pragma unroll
                     for (int cc = 0; cc < TT; ++cc) {
-                        const double2 v = vbase[cc * (D / 2) + k2];     // columns past the sequence: stale, unused
-                        const double d0 = __dsub_rn(v.x, tk0), d1 = __dsub_rn(v.y, tk1);
+                        double v0, v1, v2, v3;
+                        asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v0), "=d"(v1), "=d"(v2), "=d"(v3) : "l"(vb + voff[cc] + k4));
+                        const double d0 = __dsub_rn(v0, tk0), d1 = __dsub_rn(v1, tk1), d2 = __dsub_rn(v2, tk2), d3 = __dsub_rn(v3, tk3);
                         acc[cc] = __dadd_rn(acc[cc], __dmul_rn(d0, d0));
                         acc[cc] = __dadd_rn(acc[cc], __dmul_rn(d1, d1));
+                        acc[cc] = __dadd_rn(acc[cc], __dmul_rn(d2, d2));
+                        acc[cc] = __dadd_rn(acc[cc], __dmul_rn(d3, d3));
                     }
                 }
             }
-            // ---- column recurrence (src/dtw.jl:104-125): candidates i (stay), then i-bstep .. i-1, strict `<`
-#pragma unroll
-            for (int cc = 0; cc < TT; ++cc) {
-                if (cc < ncols) {
-                    const int t = t0 + cc;
-                    double b0 = kInf, b1 = kInf;           // costs of states 32w-2, 32w-1 after column t
-                    if (w > 0) {
-                        if (avail < t) {
-                            int a = ld_acquire_shared(done + w - 1);
-                            while (a < t) {
-                                __nanosleep(40);            // do not spend the issue slots of the working warps
-                                a = ld_acquire_shared(done + w - 1);
-                            }
-                            avail = a;
-                            __syncwarp();
-                        }
-                        if (lane < 2) {
-                            b0 = *reinterpret_cast<volatile const double*>(ring_prev + (size_t)(t % R) * 2);
-                            b1 = *reinterpret_cast<volatile const double*>(ring_prev + (size_t)(t % R) * 2 + 1);
-                        }
-                    }
-                    double c1 = __shfl_up_sync(0xFFFFFFFFu, c, 1);
-                    if (lane == 0) c1 = b1;
-                    const double oc = acc[cc];
-                    int code = BS;
-                    double minc = __dadd_rn(__dadd_rn(c, oc), 1.0);
-                    if (BS == 2) {
-                        double c2 = __shfl_up_sync(0xFFFFFFFFu, c, 2);
-                        if (lane == 0) c2 = b0;
-                        if (lane == 1) c2 = b1;
-                        const double cand = __dadd_rn(__dadd_rn(c2, oc), 2.0);
-                        if (cand < minc) { minc = cand; code = 0; }
-                    }
-                    {
-                        const double cand = __dadd_rn(c1, oc);     // transition 0: adding +0.0 is the identity
-                        if (cand < minc) { minc = cand; code = BS - 1; }
-                    }
-                    if (active) {
-                        c = minc;
-                        word |= (uint32_t)code << (BITS * (t % PER));
-                    }
-                    if ((t % PER) == PER - 1 || t == T - 1) {
-                        if (i < Spad) bpp[(int64_t)(t / PER) * Spad + i] = word;
-                        word = 0;
-                    }
-                    if (!last_warp) {
-                        if (room == 0) {                   // the slot about to be reused must have been consumed
-                            int a = ld_acquire_shared(done + w + 1);
-                            while (a < t + 2 - R) {
-                                __nanosleep(40);
-                                a = ld_acquire_shared(done + w + 1);
-                            }
-                            room = a - (t + 2 - R);
-                        } else {
-                            --room;
-                        }
-                        if (lane >= 30) ring_mine[(size_t)((t + 1) % R) * 2 + (lane - 30)] = c;
-                        __syncwarp();
-                    }
-                    // column t is consumed and column t+1 published: the counter serves the warp above as
-                    // "data ready" and the warp below as "slot free" (so the last warp counts as well)
-                    if (lane == 0) st_release_shared(done + w, t + 1);
-                }
+            // ---- hand-over, once per tile: the warp below has published the costs entering every column of
+            //      this tile; the warp above has consumed the ring positions this tile overwrites
+            if (w > 0) {
+                while (ld_acquire_shared(done + w - 1) < tend - 1) __nanosleep(64);   // do not spend the issue slots of the working warps
             }
-        }
+            if (!last_warp && t0 + TT + 1 - R > 0) {       // entering t0+TT lands where entering t0+TT-R was
+                while (ld_acquire_shared(done + w + 1) < t0 + TT + 1 - R) __nanosleep(64);
+            }
+            __syncwarp();
+            // ---- column recurrence (src/dtw.jl:104-125): candidates i (stay), then i-bstep .. i-1, strict `<`.
+            //      Lanes past the template (last warp only) run along on finite garbage: costs only travel upwards.
+            const int tb0 = t0 % R;
+            unsigned rp = rp32 + 32u * tb0;                                          // entering t0 + cc at rp + 32 cc, cc >= 1
+            unsigned wp = wp32 + 32u * (tb0 + 1);                                    // entering t0 + 1 + cc at wp + 32 cc
+            asm volatile("" : "+r"(rp), "+r"(wp));
+            double2 xn = make_double2(kInf, kInf);                                   // (c1, c2) of lanes 0 / 1 from the warp below
+            if (rd) {
+                const unsigned r0 = rp32 + 32u * (tb0 == 0 ? R : tb0);
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xn.x), "=d"(xn.y) : "r"(r0));
+            }
+            uint32_t wt = 0;
+            static_for([&](auto cc_tag) {
+                constexpr int cc = decltype(cc_tag)::value;
+                const double2 x = xn;
+                if (cc + 1 < TT && rd)                     // ahead of this column's ring store
+                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(xn.x), "=d"(xn.y) : "r"(rp), "n"(32 * (cc + 1)));
+                double c1 = __shfl_up_sync(0xFFFFFFFFu, c, 1);
+                if (lane == 0) c1 = x.x;
+                const double oc = acc[cc];
+                uint32_t cd = (uint32_t)BS << (BITS * cc);
+                double minc = __dadd_rn(__dadd_rn(c, oc), 1.0);
+                if (BS == 2) {
+                    double c2 = __shfl_up_sync(0xFFFFFFFFu, c, 2);
+                    if (lane < 2) c2 = x.y;
+                    const double cand = __dadd_rn(__dadd_rn(c2, oc), 2.0);
+                    if (cand < minc) { minc = cand; cd = 0; }
+                }
+                {
+                    const double cand = __dadd_rn(c1, oc);         // transition 0: adding +0.0 is the identity
+                    if (cand < minc) { minc = cand; cd = (uint32_t)(BS - 1) << (BITS * cc); }
+                }
+                if (FULL || cc < ncols) {
+                    c = minc;
+                    wt |= cd;
+                    if (pub) asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(wp), "n"(32 * cc), "d"(c) : "memory");
+                    if (pub31) asm volatile("st.shared.v2.f64 [%0+%1], {%2, %2};" ::"r"(wp), "n"(32 * cc + 16), "d"(c) : "memory");
+                }
+            }, std::make_integer_sequence<int, TT>{});
+            word |= wt << (BITS * TT * (tile % WPT));
+            if ((tile % WPT) == WPT - 1 || tend == T) {
+                bpp[(int64_t)(tile / WPT) * Spad + i] = word;
+                word = 0;
+            }
+            // the tile is consumed and its exit costs are published: the counter serves the warp above as "data
+            // ready" and the warp below as "positions free" (so the last warp counts as well)
+            __syncwarp();
+            if (lane == 0) st_release_shared(done + w, tend);
+        };
+        int t0 = 0, tile = 0;
+        for (; t0 + TT <= T; t0 += TT, ++tile) tile_body(std::true_type{}, t0, tile);
+        if (t0 < T) tile_body(std::false_type{}, t0, tile);
     }
-    fin[i] = c;
+    fin[i] = active ? c : kInf;
     __syncthreads();
 
     // ---- indmin(costtable[:, T+1]) -- first minimum  (src/dtw.jl:137)
     {
-        double v = active ? fin[i] : kInf;
+        double v = fin[i];
         int idx = active ? i : 0x7FFFFFFF;
         if (v != v && i != 0) v = kInf;
 #pragma unroll
@@ -510,10 +523,322 @@ static int32_t launch_dtw_pipe(const double* tmplT, const int64_t* d_toff, const
                                const int64_t* d_bpoff, const int64_t* d_order, uint32_t* bp, int64_t npairs, int maxS, int64_t* paths,
                                double* final_cost, cudaStream_t st) {
     const int nt = round_up(maxS, 32), nw = nt / 32;
-    const size_t smem = ((size_t)nw * 32 * 2 + nt + (size_t)nw * 2 * TT * DT) * sizeof(double) + (size_t)nw * sizeof(int);
+    const size_t smem = ((size_t)nw * 4 * (4 * TT + 1) + nt) * sizeof(double) + (size_t)nw * sizeof(int);
     auto k = dtw_pipe_kernel<BITS, TT, REGS, DT, BS>;
     VCB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<(unsigned)npairs, nt, smem, st>>>(tmplT, d_toff, seq, d_soff, d_bpoff, d_order, bp, paths, final_cost);
+    count_launch();
+    VCB_CUDA(cudaGetLastError());
+    return VCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// STREAM kernel: the same warp pipeline as a PERSISTENT kernel -- one CTA per SM walks a list of pairs
+// (balanced on the host by decreasing cost), and a warp that has finished its states' last tile of one
+// pair starts on the next pair at once, so the pipeline fills and drains once per LAUNCH, not once per
+// pair.  Hand-overs are mbarriers (hardware-suspended waits: a polling loop with __nanosleep overslept
+// by microseconds and the delays accumulated down the chain of warps): per warp interface a ring of
+// RT "full" (tile published) and RT "empty" (tile consumed) barriers.  Sequence tiles arrive through a
+// private cp.async double buffer one tile ahead, template values by coalesced (L1-resident) loads one
+// k-step ahead.  The final-minimum search and the back-tracking of pair q run in a SERVICE warp while
+// the compute warps are already in pair q+1 (final costs double-buffered in shared memory).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dtw_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void dtw_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void dtw_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "DTW_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DTW_DONE;\n"
+        "bra DTW_WAIT;\n"
+        "DTW_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+template <int BITS, int TT, int MAXT, int DT, int BS>
+__global__ void __launch_bounds__(MAXT, 1)
+dtw_stream_kernel(const double* __restrict__ tmpl, const int64_t* __restrict__ toff, const double* __restrict__ seq,
+                  const int64_t* __restrict__ soff, const int64_t* __restrict__ bpoff, const int32_t* __restrict__ cta_first,
+                  const int32_t* __restrict__ cta_list, uint32_t* __restrict__ bp, int64_t* __restrict__ paths,
+                  double* __restrict__ final_cost) {
+    constexpr int PER = 32 / BITS;
+    constexpr int RT = 4, R = RT * TT;           // ring: RT tiles of TT columns a warp may run ahead of its consumer
+    constexpr int RS = 4 * (R + 1);              // doubles per warp: positions 1..R of 4 doubles (see dtw_pipe_kernel)
+    constexpr int WPT = PER / TT;                // tiles per back-pointer word
+    constexpr uint32_t MASK = (1u << BITS) - 1u;
+    constexpr int D = DT;
+    static_assert(DT % 4 == 0 && (BS == 1 || BS == 2) && PER % TT == 0, "stream kernel: dimension 4n, bstep 1 or 2, fstep 0");
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nwc = ((int)blockDim.x >> 5) - 1;  // compute warps; warp nwc is the service warp
+    const int nst = nwc * 32;
+    const double kInf = __longlong_as_double(0x7FF0000000000000LL);
+
+    extern __shared__ double smem[];
+    double* ring = smem;                                   // [nwc][RS]
+    double* tiles = ring + (size_t)nwc * RS;               // [nwc][2][TT][D] private double-buffered sequence tiles
+    double* tsl = tiles + (size_t)nwc * 2 * TT * D;        // [nwc][D/2][32][2] the warp's states of the current template
+    double* fin = tsl + (size_t)nwc * 32 * D;              // [2][nst] final cost columns of pairs q, q+1
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(fin + 2 * (size_t)nst);
+    // full[nwc][RT] | empty[nwc][RT] | pairdone[2] | finfree[2]
+    const uint32_t full0 = bar0, empty0 = bar0 + 8u * nwc * RT, pairdone0 = bar0 + 16u * nwc * RT, finfree0 = pairdone0 + 16u;
+    if (threadIdx.x == 0) {
+        for (int e = 0; e < 2 * nwc * RT; ++e) dtw_mbar_init(bar0 + 8u * e, 1);
+        dtw_mbar_init(pairdone0, nwc);
+        dtw_mbar_init(pairdone0 + 8u, nwc);
+        dtw_mbar_init(finfree0, 1);
+        dtw_mbar_init(finfree0 + 8u, 1);
+    }
+    __syncthreads();
+    const int lbeg = cta_first[blockIdx.x], npl = cta_first[blockIdx.x + 1] - lbeg;
+
+    if (w == nwc) {
+        // ================= service warp: indmin + backward of finished pairs (src/dtw.jl:137-142) =================
+        for (int q = 0; q < npl; ++q) {
+            const int p = cta_list[lbeg + q];
+            const int64_t sb = soff[p];
+            const int S = (int)(toff[p + 1] - toff[p]);
+            const int T = (int)(soff[p + 1] - sb);
+            const int Spad = (S + 31) & ~31;
+            const uint32_t* bpp = bp + bpoff[p];
+            dtw_mbar_wait(pairdone0 + 8u * (q & 1), (q >> 1) & 1);
+            const double* f = fin + (size_t)(q & 1) * nst;
+            double v = kInf;
+            int idx = 0x7FFFFFFF;
+            for (int j = lane; j < S; j += 32) {
+                double vj = f[j];
+                if (vj != vj && j != 0) vj = kInf;       // see dtw_fused_kernel
+                if (vj < v || idx == 0x7FFFFFFF) { v = vj; idx = j; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                double ov = __shfl_down_sync(0xFFFFFFFFu, v, o);
+                int oi = __shfl_down_sync(0xFFFFFFFFu, idx, o);
+                if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+            }
+            int st = __shfl_sync(0xFFFFFFFFu, idx, 0);
+            if (lane == 0 && final_cost) final_cost[p] = v;
+            __syncwarp();
+            if (lane == 0) dtw_mbar_arrive(finfree0 + 8u * (q & 1));      // the final costs are consumed
+            int64_t* path = paths + sb;
+            if (lane == 0) path[T - 1] = st + 1;
+            int cur_wi = -1, wbase = 0;
+            uint32_t wd = 0;
+            for (int t = T - 1; t >= 1; --t) {
+                const int wi = t / PER;
+                if (wi != cur_wi || st < wbase || st >= wbase + 32) {
+                    wbase = max(0, min(st - 31, Spad - 32));
+                    wd = bpp[(int64_t)wi * Spad + wbase + lane];
+                    cur_wi = wi;
+                }
+                const uint32_t ww = __shfl_sync(0xFFFFFFFFu, wd, st - wbase);
+                const int code = (int)((ww >> (BITS * (t % PER))) & MASK);
+                st = st + code - BS;
+                if (lane == 0) path[t - 1] = st + 1;
+            }
+        }
+        return;
+    }
+
+    // ======================================= compute warps =======================================
+    const int i = w * 32 + lane;
+    uint32_t g_in = 0, g_out = 0;                // tiles taken from the warp below / handed to the warp above so far
+    uint32_t rp32 = (uint32_t)__cvta_generic_to_shared(ring + (size_t)(w > 0 ? w - 1 : 0) * RS + 2 * lane);    // lanes 0, 1 read
+    uint32_t wp32 = (uint32_t)__cvta_generic_to_shared(ring + (size_t)w * RS + (lane == 30 ? 1 : 0));
+    asm volatile("" : "+r"(rp32), "+r"(wp32));
+    double* const mytiles = tiles + (size_t)w * 2 * TT * D;
+    const double2* const mytmpl = reinterpret_cast<const double2*>(tsl + (size_t)w * 32 * D) + lane;     // dims 2j, 2j+1 at [32 j]
+    for (int q = 0; q < npl; ++q) {
+        const int p = cta_list[lbeg + q];
+        const int64_t tb = toff[p], sb = soff[p];
+        const int S = (int)(toff[p + 1] - tb);
+        const int T = (int)(soff[p + 1] - sb);
+        if (q >= 2) dtw_mbar_wait(finfree0 + 8u * (q & 1), ((q >> 1) - 1) & 1);     // the service warp is done with pair q-2
+        if (32 * w >= S) {                       // no state of this pair in this warp
+            if (lane == 0) dtw_mbar_arrive(pairdone0 + 8u * (q & 1));
+            continue;
+        }
+        const bool below = w > 0, above = 32 * (w + 1) < S;
+        const bool rd = below && lane < 2, pub = above && lane >= 30, pub31 = above && lane == 31;
+        const int Spad = (S + 31) & ~31;
+        uint32_t* const bpp = bp + bpoff[p] + i;
+        {   // this warp's 32 template frames, straight from the caller's (D, S) matrix (lanes past the template
+            // repeat its last state); lands with the first sequence tile
+            const double* src = tmpl + (tb + min(i, S - 1)) * D;
+#pragma unroll
+            for (int j = 0; j < D / 2; ++j) {
+                const unsigned a = (unsigned)__cvta_generic_to_shared(mytmpl + 32 * j);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(src + 2 * j) : "memory");
+            }
+        }
+        const double* const srow = seq + sb * D;
+        double c = (double)(i + 1);              // src/dtw.jl:49  costtable[:,1] = 1:S
+        uint32_t word = 0;
+        auto fetch_tile = [&](int t0n, int buf) {
+            if (t0n < T) {
+                const int pieces = min(TT, T - t0n) * (D / 2);
+                const double* src = srow + (size_t)t0n * D;
+                for (int e = lane; e < pieces; e += 32) {
+                    const unsigned a = (unsigned)__cvta_generic_to_shared(mytiles + (size_t)buf * TT * D + 2 * e);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(src + 2 * e) : "memory");
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto tile_body = [&](auto full_tag, const int t0, const int tile) {
+            constexpr bool FULL = decltype(full_tag)::value;
+            const int ncols = FULL ? TT : T - t0;
+            fetch_tile(t0 + TT, (tile + 1) & 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            __syncwarp();
+            // ---- observation costs for TT frames: strict left-to-right Float64 sum, no FMA (src/dtw.jl:33-35)
+            double acc[TT];
+#pragma unroll
+            for (int cc = 0; cc < TT; ++cc) acc[cc] = 0.0;
+            {
+                const double2* vb = reinterpret_cast<const double2*>(mytiles + (size_t)(tile & 1) * TT * D);
+                double2 ta = mytmpl[0], tc = mytmpl[32];
+#pragma unroll
+                for (int k4 = 0; k4 < D; k4 += 4) {
+                    double2 na = ta, nc = tc;
+                    if (k4 + 4 < D) { na = mytmpl[32 * (k4 / 2 + 2)]; nc = mytmpl[32 * (k4 / 2 + 3)]; }     // a k-step ahead
+#pragma unroll
+                    for (int cc = 0; cc < TT; ++cc) {       // columns past the sequence: stale tile data, results unused
+                        const double2 va = vb[cc * (D / 2) + k4 / 2], vc = vb[cc * (D / 2) + k4 / 2 + 1];
+                        const double d0 = __dsub_rn(va.x, ta.x), d1 = __dsub_rn(va.y, ta.y);
+                        const double d2 = __dsub_rn(vc.x, tc.x), d3 = __dsub_rn(vc.y, tc.y);
+                        // (0.0 + d0^2 is d0^2: a square is never -0.0)
+                        acc[cc] = k4 == 0 ? __dmul_rn(d0, d0) : __dadd_rn(acc[cc], __dmul_rn(d0, d0));
+                        acc[cc] = __dadd_rn(acc[cc], __dmul_rn(d1, d1));
+                        acc[cc] = __dadd_rn(acc[cc], __dmul_rn(d2, d2));
+                        acc[cc] = __dadd_rn(acc[cc], __dmul_rn(d3, d3));
+                    }
+                    ta = na; tc = nc;
+                }
+            }
+            // ---- hand-over, once per tile: the warp below has published the costs entering every column of
+            //      this tile; the warp above has consumed the ring positions this tile overwrites
+            const uint32_t sin = g_in & (RT - 1), sout = g_out & (RT - 1);
+            if (below) dtw_mbar_wait(full0 + 8u * ((w - 1) * RT + sin), (g_in / RT) & 1);
+            if (above && g_out >= RT) dtw_mbar_wait(empty0 + 8u * (w * RT + sout), (g_out / RT - 1) & 1);
+            // (c1, c2) of lanes 0 / 1 entering the first column: the initial column of a pair is known
+            // (src/dtw.jl:49), later ones sit in the last position of the previous ring stage
+            double2 xn = make_double2(kInf, kInf);
+            if (below) {
+                if (tile == 0) xn = make_double2((double)(32 * w), lane == 0 ? (double)(32 * w - 1) : (double)(32 * w));
+                else if (rd) {
+                    const unsigned r0 = rp32 + 32u * (sin == 0 ? R : TT * sin);
+                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xn.x), "=d"(xn.y) : "r"(r0));
+                }
+                if (g_in >= 1) {                 // the previous stage of the ring is consumed
+                    __syncwarp();
+                    if (lane == 0) dtw_mbar_arrive(empty0 + 8u * ((w - 1) * RT + ((g_in - 1) & (RT - 1))));
+                }
+            }
+            // ---- column recurrence (src/dtw.jl:104-125): candidates i (stay), then i-bstep .. i-1, strict `<`.
+            //      Lanes past the template (last warp only) run along on finite garbage: costs only travel upwards.
+            unsigned rp = rp32 + 32u * (TT * sin);                                   // entering t0 + cc at rp + 32 cc, cc >= 1
+            unsigned wp = wp32 + 32u * (TT * sout + 1);                              // entering t0 + 1 + cc at wp + 32 cc
+            asm volatile("" : "+r"(rp), "+r"(wp));
+            uint32_t wt = 0;
+            static_for([&](auto cc_tag) {
+                constexpr int cc = decltype(cc_tag)::value;
+                const double2 x = xn;
+                if (cc + 1 < TT && rd)                     // ahead of this column's ring store
+                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(xn.x), "=d"(xn.y) : "r"(rp), "n"(32 * (cc + 1)));
+                double c1 = __shfl_up_sync(0xFFFFFFFFu, c, 1);
+                if (lane == 0) c1 = x.x;
+                const double oc = acc[cc];
+                uint32_t cd = (uint32_t)BS << (BITS * cc);
+                double minc = __dadd_rn(__dadd_rn(c, oc), 1.0);
+                if (BS == 2) {
+                    double c2 = __shfl_up_sync(0xFFFFFFFFu, c, 2);
+                    if (lane < 2) c2 = x.y;
+                    const double cand = __dadd_rn(__dadd_rn(c2, oc), 2.0);
+                    if (cand < minc) { minc = cand; cd = 0; }
+                }
+                {
+                    const double cand = __dadd_rn(c1, oc);         // transition 0: adding +0.0 is the identity
+                    if (cand < minc) { minc = cand; cd = (uint32_t)(BS - 1) << (BITS * cc); }
+                }
+                if (FULL || cc < ncols) {
+                    c = minc;
+                    wt |= cd;
+                    if (pub) asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(wp), "n"(32 * cc), "d"(c) : "memory");
+                    if (pub31) asm volatile("st.shared.v2.f64 [%0+%1], {%2, %2};" ::"r"(wp), "n"(32 * cc + 16), "d"(c) : "memory");
+                }
+            }, std::make_integer_sequence<int, TT>{});
+            // the tile's exit costs are published
+            if (above) {
+                __syncwarp();
+                if (lane == 0) dtw_mbar_arrive(full0 + 8u * (w * RT + sout));
+            }
+            g_in += below ? 1u : 0u;
+            g_out += above ? 1u : 0u;
+            word |= wt << (BITS * TT * (tile % WPT));
+            if ((tile % WPT) == WPT - 1 || t0 + ncols == T) {
+                bpp[(int64_t)(tile / WPT) * Spad] = word;
+                word = 0;
+            }
+        };
+        fetch_tile(0, 0);
+        int t0 = 0, tile = 0;
+        for (; t0 + TT <= T; t0 += TT, ++tile) tile_body(std::true_type{}, t0, tile);
+        if (t0 < T) tile_body(std::false_type{}, t0, tile);
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        fin[(size_t)(q & 1) * nst + i] = (i < S) ? c : kInf;
+        __syncwarp();
+        if (lane == 0) dtw_mbar_arrive(pairdone0 + 8u * (q & 1));         // after the back-pointer stores of the whole warp
+    }
+}
+
+// pairs -> CTAs: longest processing time first (pairs sorted by decreasing cost, each to the least loaded CTA)
+static void dtw_balance(const std::vector<int64_t>& order, const int64_t* h_toff, const int64_t* h_soff, int nb,
+                        std::vector<int32_t>& first, std::vector<int32_t>& list) {
+    std::vector<std::vector<int32_t>> bins(nb);
+    std::vector<std::pair<int64_t, int>> heap;      // (-load, bin): max-heap on -load = min-heap on load
+    for (int b = 0; b < nb; ++b) heap.push_back({0, -b});
+    std::make_heap(heap.begin(), heap.end());
+    for (int64_t p : order) {
+        std::pop_heap(heap.begin(), heap.end());
+        auto& top = heap.back();
+        bins[-top.second].push_back((int32_t)p);
+        top.first -= (h_toff[p + 1] - h_toff[p]) * (h_soff[p + 1] - h_soff[p]);
+        std::push_heap(heap.begin(), heap.end());
+    }
+    first.assign(nb + 1, 0);
+    list.clear();
+    for (int b = 0; b < nb; ++b) {
+        list.insert(list.end(), bins[b].begin(), bins[b].end());
+        first[b + 1] = (int32_t)list.size();
+    }
+}
+
+// shared memory of the stream kernel with nwc compute warps: hand-over ring, private sequence tiles, template
+// slices, two final cost columns, mbarriers
+static size_t dtw_stream_smem(int nwc, int D, int TT) {
+    return ((size_t)nwc * 4 * (4 * TT + 1) + (size_t)nwc * 2 * TT * D + (size_t)nwc * 32 * D + 2 * (size_t)nwc * 32) * sizeof(double) +
+           (size_t)(2 * nwc * 4 + 4) * sizeof(uint64_t);
+}
+static bool dtw_stream_fits(int maxS, int D, int TT) {
+    const int nwc = (maxS + 31) / 32;
+    return nwc + 1 <= 22 && dtw_stream_smem(nwc, D, TT) <= 227 * 1024;
+}
+
+template <int BITS, int TT, int MAXT, int DT, int BS>
+static int32_t launch_dtw_stream(const double* tmpl, const int64_t* d_toff, const double* seq, const int64_t* d_soff,
+                                 const int64_t* d_bpoff, const int32_t* d_first, const int32_t* d_list, int nb, uint32_t* bp,
+                                 int maxS, int64_t* paths, double* final_cost, cudaStream_t st) {
+    const int nwc = (maxS + 31) / 32, nt = (nwc + 1) * 32;
+    const size_t smem = dtw_stream_smem(nwc, DT, TT);
+    auto k = dtw_stream_kernel<BITS, TT, MAXT, DT, BS>;
+    VCB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)nb, nt, smem, st>>>(tmpl, d_toff, seq, d_soff, d_bpoff, d_first, d_list, bp, paths, final_cost);
     count_launch();
     VCB_CUDA(cudaGetLastError());
     return VCB_OK;
@@ -533,9 +858,10 @@ static int32_t launch_dtw(const double* tmplT, const int64_t* d_toff, const doub
     // cycles: release store, acquire poll, ring read) than one __syncthreads of 21 warps (~100), and the
     // warps of a CTA still move through observation and recurrence phases together.  Kept as an experiment.
     static const int pipe = [] { const char* e = getenv("VCB_DTW_PIPE"); return e ? atoi(e) : 0; }();
-    if constexpr (DT > 0 && DT % 2 == 0 && FS == 0 && (BS == 1 || BS == 2) && BITS == 2) {
-        if (pipe && nt <= 672) return launch_dtw_pipe<BITS, 8, 48, DT, BS>(tmplT, d_toff, seq, d_soff, d_bpoff, d_order, bp, npairs, maxS, paths, final_cost, st);
-        if (pipe && nt <= 1024) return launch_dtw_pipe<BITS, 8, 64, DT, BS>(tmplT, d_toff, seq, d_soff, d_bpoff, d_order, bp, npairs, maxS, paths, final_cost, st);
+    if constexpr (DT > 0 && DT % 4 == 0 && FS == 0 && (BS == 1 || BS == 2) && BITS == 2) {
+        const bool aligned = (reinterpret_cast<uintptr_t>(seq) & 31) == 0;      // 32-byte frame loads
+        if (pipe && aligned && nt <= 672) return launch_dtw_pipe<BITS, 8, 48, DT, BS>(tmplT, d_toff, seq, d_soff, d_bpoff, d_order, bp, npairs, maxS, paths, final_cost, st);
+        if (pipe && aligned && nt <= 1024) return launch_dtw_pipe<BITS, 8, 64, DT, BS>(tmplT, d_toff, seq, d_soff, d_bpoff, d_order, bp, npairs, maxS, paths, final_cost, st);
     }
     // <= 672 states and a compile-time dimension: two CTAs per SM (8-column tiles, 48 registers): one
     // CTA's barrier-paced recurrence overlaps the other's FP64-bound observation costs (the
@@ -615,7 +941,6 @@ int32_t dtw_fit_batch_device(const double* d_tmpl, const int64_t* h_toff, const 
     uint32_t* d_bp = nullptr;
     const size_t noff = (size_t)(npairs + 1);
     VCB_CUDA(cudaMallocAsync((void**)&d_off, 4 * noff * sizeof(int64_t), st));
-    VCB_CUDA(cudaMallocAsync((void**)&d_tmplT, (size_t)totalS * D * sizeof(double), st));
     VCB_CUDA(cudaMallocAsync((void**)&d_bp, (size_t)std::max<int64_t>(bpoff[npairs], 1) * sizeof(uint32_t), st));
     // offsets are tiny; pageable async copies complete before return of the call for the host
     // buffers involved (they are staged by the driver), bpoff lives until we synchronise below.
@@ -623,6 +948,38 @@ int32_t dtw_fit_batch_device(const double* d_tmpl, const int64_t* h_toff, const 
     VCB_CUDA(cudaMemcpyAsync(d_off + noff, h_soff, noff * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     VCB_CUDA(cudaMemcpyAsync(d_off + 2 * noff, bpoff.data(), noff * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     VCB_CUDA(cudaMemcpyAsync(d_off + 3 * noff, order.data(), (size_t)npairs * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    int32_t rc;
+    // Persistent stream kernel: the reference's own windows, the common dimensions, templates whose warp slices fit
+    // in shared memory (D = 24: up to 672 frames), 16-byte aligned matrices.  VCB_DTW_PIPE=0 keeps the barrier kernel.
+    static const int pipe_mode = [] { const char* e = getenv("VCB_DTW_PIPE"); return e ? atoi(e) : 0; }();
+    if (pipe_mode == 2 && fstep == 0 && (bstep == 1 || bstep == 2) && (D == 24 || D == 40) && dtw_stream_fits(maxS, D, 8) &&
+        ((reinterpret_cast<uintptr_t>(d_seq) | reinterpret_cast<uintptr_t>(d_tmpl)) & 15) == 0) {
+        int dev = 0, nsm = 0;
+        VCB_CUDA(cudaGetDevice(&dev));
+        VCB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+        const int nb = (int)std::min<int64_t>(npairs, nsm);
+        std::vector<int32_t> first, list;
+        dtw_balance(order, h_toff, h_soff, nb, first, list);
+        int32_t* d_lists = nullptr;
+        VCB_CUDA(cudaMallocAsync((void**)&d_lists, (size_t)(nb + 1 + npairs) * sizeof(int32_t), st));
+        VCB_CUDA(cudaMemcpyAsync(d_lists, first.data(), (size_t)(nb + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        VCB_CUDA(cudaMemcpyAsync(d_lists + nb + 1, list.data(), (size_t)npairs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        stage_begin(st);
+        stage_mark(st);      // [0] (no template transpose on this path); [1] the stream kernel
+#define VCB_DTW_STREAM(MAXT, DT, BS) launch_dtw_stream<2, 8, MAXT, DT, BS>(d_tmpl, d_off, d_seq, d_off + noff, d_off + 2 * noff, d_lists, d_lists + nb + 1, nb, d_bp, maxS, d_paths, d_final_cost, st)
+        // at most 21 compute warps + the service warp fit (shared memory): 704 threads, 80 registers each
+        if (D == 24 && bstep == 2) rc = VCB_DTW_STREAM(704, 24, 2);
+        else if (D == 24) rc = VCB_DTW_STREAM(704, 24, 1);
+        else if (bstep == 2) rc = VCB_DTW_STREAM(704, 40, 2);
+        else rc = VCB_DTW_STREAM(704, 40, 1);
+#undef VCB_DTW_STREAM
+        stage_mark(st);
+        cudaFreeAsync(d_lists, st);
+        cudaFreeAsync(d_off, st);
+        cudaFreeAsync(d_bp, st);
+        return rc;
+    }
+    VCB_CUDA(cudaMallocAsync((void**)&d_tmplT, (size_t)totalS * D * sizeof(double), st));
     stage_begin(st);
     {
         dim3 grid((unsigned)npairs, (maxS + 31) / 32), block(32, 8);
@@ -631,7 +988,6 @@ int32_t dtw_fit_batch_device(const double* d_tmpl, const int64_t* h_toff, const 
         VCB_CUDA(cudaGetLastError());
     }
     stage_mark(st);      // [0] template transpose; [1] the fused kernel
-    int32_t rc;
 #define VCB_DTW_CALL d_tmplT, d_off, d_seq, d_off + noff, d_off + 2 * noff, d_off + 3 * noff, d_bp, D, fstep, bstep, npairs, maxS, d_paths, d_final_cost, st
     if (fstep == 0 && bstep == 1) rc = launch_dtw_dim<2, 1, 0>(VCB_DTW_CALL);
     else if (fstep == 0 && bstep == 2) rc = launch_dtw_dim<2, 2, 0>(VCB_DTW_CALL);
