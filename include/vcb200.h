@@ -76,7 +76,8 @@ int32_t vcb_host_free(void* ptr);
 int32_t vcb_host_register(void* ptr, size_t bytes);
 int32_t vcb_host_unregister(void* ptr);
 /* Kernel selection for the posterior/conditional-mean stage: 0 = auto, 1 = CUDA-core fp32 kernel,
- * 2 = tcgen05 3xTF32 kernel.  Process-wide; intended for tests and profiling. */
+ * 2 = tcgen05 3xTF32 kernel.  Variant 1 also routes DTW through the per-column barrier kernel instead of
+ * the persistent warp-pipeline kernel.  Process-wide; intended for tests and profiling. */
 int32_t vcb_set_kernel_variant(int32_t variant);
 /* Number of kernel launches issued by this library since process start (bench bookkeeping). */
 int64_t vcb_launch_count(void);

@@ -10,6 +10,16 @@ from conftest import GOLDEN
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=[0, 1], ids=["stream", "barrier"])
+def dtw_kernel(request, vcb):
+    """Every test runs twice: with the default kernel choice (the persistent warp-pipeline kernel where it
+    applies: fstep 0, bstep 1 / 2, D = 24 / 40, templates of up to 672 / 416 frames) and with the per-column
+    barrier kernel everywhere (variant 1).  Both must be bit-exact with the oracle."""
+    vcb.set_kernel_variant(request.param)
+    yield request.param
+    vcb.set_kernel_variant(0)
+
+
 def test_reference_known_answers(vcb):
     for c in json.load(open(os.path.join(GOLDEN, "dtw_reference_tests.json"))):
         d = vcb.DTWs.DTW(bstep=c["bstep"], fstep=c["fstep"])
@@ -60,13 +70,16 @@ def test_ragged_and_tiny_compile_time_dimension(vcb, oracle):
             paths, fc = vcb.DTWs.fit_batch(vcb.DTWs.DTW(fstep=fs, bstep=bs), tm, to, sq, so)
             ref, rfc = oracle.dtw_fit_batch(tm, to, sq, so, fs, bs)
             assert np.array_equal(paths, ref) and np.array_equal(fc, rfc), (D, fs, bs)
-        # short templates only: the CTA is a few warps wide (<= 672 threads takes the two-CTA build)
-        sel = [i for i in range(len(S)) if S[i] <= 97]
-        to2 = np.concatenate([[0], np.cumsum([S[i] for i in sel])]); so2 = np.concatenate([[0], np.cumsum([T[i] for i in sel])])
-        tm2 = np.concatenate([tm[:, to[i]:to[i + 1]] for i in sel], 1); sq2 = np.concatenate([sq[:, so[i]:so[i + 1]] for i in sel], 1)
-        paths, fc = vcb.DTWs.fit_batch(vcb.DTWs.DTW(fstep=0, bstep=2), tm2, to2, sq2, so2)
-        ref, rfc = oracle.dtw_fit_batch(tm2, to2, sq2, so2, 0, 2)
-        assert np.array_equal(paths, ref) and np.array_equal(fc, rfc), D
+        # templates of up to 672 / 97 frames only: the batch maximum decides the kernel and the CTA width
+        # (D = 24: 21 + 1 warps of the stream kernel; a few warps)
+        for smax in (672, 97):
+          sel = [i for i in range(len(S)) if S[i] <= smax]
+          to2 = np.concatenate([[0], np.cumsum([S[i] for i in sel])]); so2 = np.concatenate([[0], np.cumsum([T[i] for i in sel])])
+          tm2 = np.concatenate([tm[:, to[i]:to[i + 1]] for i in sel], 1); sq2 = np.concatenate([sq[:, so[i]:so[i + 1]] for i in sel], 1)
+          for bs in (1, 2):
+            paths, fc = vcb.DTWs.fit_batch(vcb.DTWs.DTW(fstep=0, bstep=bs), tm2, to2, sq2, so2)
+            ref, rfc = oracle.dtw_fit_batch(tm2, to2, sq2, so2, 0, bs)
+            assert np.array_equal(paths, ref) and np.array_equal(fc, rfc), (D, smax, bs)
 
 
 @pytest.mark.parametrize("S,T", [(1025, 40), (1500, 300), (2500, 120), (4097, 33), (8192, 17)])

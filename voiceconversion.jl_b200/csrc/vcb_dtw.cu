@@ -286,263 +286,38 @@ static int32_t launch_dtw_cfg(const double* tmplT, const int64_t* d_toff, const 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Barrier-free variant for the reference's own windows (fstep = 0, bstep = 1 or 2): dependencies then
-// run one way only, from lower to higher template states, so the warps of a CTA form a PIPELINE whose
-// unit of hand-over is a TILE of TT columns.  A thread keeps the cost of its state in a register; inside
-// a tile the two neighbours below come by shuffle, and lanes 0/1 take them from a shared-memory ring in
-// which every warp publishes the costs of its last two states for each column of a tile, followed by ONE
-// release store of its progress counter per tile.  Warp w starts the recurrence of tile n when warp w-1
-// has finished it (one acquire poll per tile) and computes the observation costs of the tile -- the
-// FP64-bound part, which depends on nobody -- before it asks, so in the steady state the warps sit one
-// recurrence apart and the FP64 pipe always finds warps in their observation phase: there is no CTA-wide
-// barrier to drain it (the per-column __syncthreads of dtw_fused_kernel is its largest stall).
-// (Round 2's first version handed over every COLUMN: a release store, an acquire poll and a ring read
-// per column cost ~350 cycles against ~100 for a __syncthreads, 4.41 vs 2.79 ms; per tile the same
-// hand-over is amortised over TT columns.)  Bit-exact: same candidate order, same strict `<`.
+// STREAM kernel -- the default for the reference's own windows (fstep = 0, bstep = 1 or 2), D = 24 / 40 and
+// templates whose warp slices fit in shared memory.  Dependencies then run one way only, from lower to
+// higher template states, so the warps of a CTA form a PIPELINE whose unit of hand-over is a TILE of TT
+// columns: warp w owns states 32w .. 32w+31 (one per lane, cost in a register); inside a tile the two
+// neighbours below come by shuffle, and lanes 0/1 take them from a shared-memory ring in which the warp
+// below publishes the costs of its last two states for every column of a tile, followed by ONE mbarrier
+// arrival.  Warp w starts the recurrence of tile n when warp w-1 has finished it and computes the
+// observation costs of the tile -- the FP64-bound part, which depends on nobody -- before it asks, so the
+// warps sit one recurrence apart and the FP64 pipe always finds warps in their observation phase; there is
+// no CTA-wide barrier to drain it (the per-column __syncthreads of dtw_fused_kernel is its largest stall).
+// The kernel is PERSISTENT: one CTA per SM walks a list of pairs (balanced on the host by decreasing cost),
+// and a warp that has finished the last tile of one pair starts on the next pair at once, so the pipeline
+// fills and drains once per LAUNCH, not once per pair.  Hand-overs are mbarriers: per warp interface a ring
+// of RT "full" (tile published) and RT "empty" (tile consumed) barriers.  Sequence tiles arrive through a
+// private cp.async double buffer one tile ahead; the warp's 32 template frames sit in shared memory for
+// the whole pair, copied straight from the caller's (D, S) matrix (no transposed copy on this path).  The
+// final-minimum search and the back-tracking of pair q run in a SERVICE warp while the compute warps are
+// already in pair q+1 (final costs double-buffered in shared memory).  Bit-exact: same candidate order,
+// same strict `<`, same left-to-right sums.
+// History (round 2, all bit-exact, C3 = 1000 pairs of ~600 x 600): hand-over per COLUMN through flags
+// 4.41 ms; per tile through flags polled with __nanosleep, one CTA per pair 6.0 ms (a 21-warp CTA at 48
+// registers does not fit twice on an SM -- six warps land on one sub-partition -- and the sleeps overshoot);
+// persistent + mbarriers + template by global loads 2.80 ms; template slices in shared memory 2.49 ms
+// (barrier kernel 2.72 ms).  What remains is the integer number of warps per SM sub-partition: a pair with
+// 21 (18) active warps loads the four FP64 pipes 6/5/5/5 (5/5/4/4) and the chain runs at the pace of the
+// fullest one (17 % of the warp time is spent waiting for the warp below; a one-tile lookahead with
+// 4-column tiles did not change that and cost 8 % in hand-overs).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int ld_acquire_shared(const volatile int* p) {
-    int v;
-    const unsigned a = (unsigned)__cvta_generic_to_shared(const_cast<const int*>(p));
-    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_shared(volatile int* p, int v) {
-    const unsigned a = (unsigned)__cvta_generic_to_shared(const_cast<int*>(p));
-    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
-}
-
 // f(integral_constant<int, 0>) ... f(integral_constant<int, N-1>): loop indices usable as asm immediates
 template <class F, int... I>
 __device__ __forceinline__ void static_for(F&& f, std::integer_sequence<int, I...>) { (f(std::integral_constant<int, I>{}), ...); }
 
-template <int BITS, int TT, int REGS, int DT, int BS>
-__global__ void __maxnreg__(REGS)
-dtw_pipe_kernel(const double* __restrict__ tmplT, const int64_t* __restrict__ toff, const double* __restrict__ seq,
-                const int64_t* __restrict__ soff, const int64_t* __restrict__ bpoff, const int64_t* __restrict__ order,
-                uint32_t* __restrict__ bp, int64_t* __restrict__ paths, double* __restrict__ final_cost) {
-    constexpr int PER = 32 / BITS;
-    constexpr int RT = 4, R = RT * TT;           // ring: RT tiles of TT columns a warp may run ahead of its consumer
-    constexpr int RS = 4 * (R + 1);              // doubles per warp: positions 1..R of 4 doubles (position 0 unused)
-    constexpr int WPT = PER / TT;                // tiles per back-pointer word
-    constexpr uint32_t MASK = (1u << BITS) - 1u;
-    static_assert(DT % 4 == 0 && (BS == 1 || BS == 2), "pipeline kernel: dimension 4n, bstep 1 or 2, fstep 0");
-    static_assert(PER % TT == 0, "a back-pointer word is a whole number of tiles");
-    constexpr int D = DT;
-    const int p = (int)order[blockIdx.x];
-    const int64_t tb = toff[p], sb = soff[p];
-    const int S = (int)(toff[p + 1] - tb);
-    const int T = (int)(soff[p + 1] - sb);
-    const int i = threadIdx.x, lane = i & 31, w = i >> 5, nw = blockDim.x >> 5;
-    const bool active = i < S;
-    const int Spad = (S + 31) & ~31;
-    uint32_t* bpp = bp + bpoff[p];
-    const double kInf = __longlong_as_double(0x7FF0000000000000LL);
-
-    // ring[w][pos][4], pos = 1..R: the costs of the warp's last two states ENTERING column t sit at position
-    // ((t - 1) mod R) + 1 as [b1, b0, b1, b1] (b0: lane 30, b1: lane 31), so that lane 0 of the warp above reads
-    // (c1, c2) = (b1, b0) and lane 1 reads (-, c2) = (b1, b1) with one 16-byte load each, the positions a tile
-    // WRITES are contiguous (entering t0+1 .. t0+TT) and so are the ones it READS, except the first.
-    extern __shared__ double smem[];
-    double* ring = smem;
-    double* fin = smem + (size_t)nw * RS;                  // [blockDim] final cost column
-    volatile int* done = reinterpret_cast<volatile int*>(fin + blockDim.x);   // [nw] columns published
-    __shared__ double red_v[32];
-    __shared__ int red_i[32];
-    __shared__ int s_best;
-
-    double c = active ? (double)(i + 1) : kInf;            // src/dtw.jl:49  costtable[:,1] = 1:S
-    {
-        double* e0 = ring + (size_t)w * RS + 4 * R;        // entering column 0
-        if (lane == 30) e0[1] = c;
-        if (lane == 31) { e0[0] = c; e0[2] = c; e0[3] = c; }
-    }
-    if (lane == 0) done[w] = (32 * w < S) ? 0 : 0x7FFFFFFF;     // warps without a state never hold anyone up
-    __syncthreads();
-    if (32 * w < S) {
-        const double* tcol = tmplT + tb * D + i;           // element k at tcol[k * S]
-        // ring addresses as opaque 32-bit shared-memory offsets: one register each, immediate offsets per column
-        // (with generic pointers the compiler re-derives every address from scratch at this register budget)
-        unsigned rp32 = (unsigned)__cvta_generic_to_shared(ring + (size_t)(w > 0 ? w - 1 : 0) * RS + 2 * lane);    // lanes 0, 1 read
-        unsigned wp32 = (unsigned)__cvta_generic_to_shared(ring + (size_t)w * RS + (lane == 30 ? 1 : 0));
-        asm volatile("" : "+r"(rp32), "+r"(wp32));
-        const bool last_warp = 32 * (w + 1) >= S;          // nobody consumes this warp's boundary
-        const bool rd = w > 0 && lane < 2;
-        const bool pub = !last_warp && lane >= 30, pub31 = !last_warp && lane == 31;
-        uint32_t word = 0;
-        const double* srow = seq + sb * D;                 // frames are read as warp-uniform (L1-resident) loads
-
-        auto tile_body = [&](auto full_tag, const int t0, const int tile) {
-            constexpr bool FULL = decltype(full_tag)::value;
-            const int ncols = FULL ? TT : T - t0;
-            const int tend = t0 + ncols;
-            // ---- observation costs for TT frames: strict left-to-right Float64 sum, no FMA (src/dtw.jl:33-35)
-            double acc[TT];
-#pragma unroll
-            for (int cc = 0; cc < TT; ++cc) acc[cc] = 0.0;
-            if (active) {
-                const double* tp = tcol;
-                const double* vb = srow + (size_t)t0 * D;
-                int voff[TT];                              // partial tile: columns past the sequence re-read its last frame
-#pragma unroll
-                for (int cc = 0; cc < TT; ++cc) voff[cc] = (FULL ? cc : min(cc, ncols - 1)) * D;
-                // four dimensions of a frame per 32-byte load (sm_100: LDG.256; rows of D = 4n doubles keep the alignment)
-#pragma unroll 1
-                for (int k4 = 0; k4 < D; k4 += 4) {
-                    const double tk0 = tp[0], tk1 = tp[S], tk2 = tp[2 * (size_t)S], tk3 = tp[3 * (size_t)S];
-                    tp += 4 * (size_t)S;
-#pragma unroll
-                    for (int cc = 0; cc < TT; ++cc) {
-                        double v0, v1, v2, v3;
-                        asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v0), "=d"(v1), "=d"(v2), "=d"(v3) : "l"(vb + voff[cc] + k4));
-                        const double d0 = __dsub_rn(v0, tk0), d1 = __dsub_rn(v1, tk1), d2 = __dsub_rn(v2, tk2), d3 = __dsub_rn(v3, tk3);
-                        acc[cc] = __dadd_rn(acc[cc], __dmul_rn(d0, d0));
-                        acc[cc] = __dadd_rn(acc[cc], __dmul_rn(d1, d1));
-                        acc[cc] = __dadd_rn(acc[cc], __dmul_rn(d2, d2));
-                        acc[cc] = __dadd_rn(acc[cc], __dmul_rn(d3, d3));
-                    }
-                }
-            }
-            // ---- hand-over, once per tile: the warp below has published the costs entering every column of
-            //      this tile; the warp above has consumed the ring positions this tile overwrites
-            if (w > 0) {
-                while (ld_acquire_shared(done + w - 1) < tend - 1) __nanosleep(64);   // do not spend the issue slots of the working warps
-            }
-            if (!last_warp && t0 + TT + 1 - R > 0) {       // entering t0+TT lands where entering t0+TT-R was
-                while (ld_acquire_shared(done + w + 1) < t0 + TT + 1 - R) __nanosleep(64);
-            }
-            __syncwarp();
-            // ---- column recurrence (src/dtw.jl:104-125): candidates i (stay), then i-bstep .. i-1, strict `<`.
-            //      Lanes past the template (last warp only) run along on finite garbage: costs only travel upwards.
-            const int tb0 = t0 % R;
-            unsigned rp = rp32 + 32u * tb0;                                          // entering t0 + cc at rp + 32 cc, cc >= 1
-            unsigned wp = wp32 + 32u * (tb0 + 1);                                    // entering t0 + 1 + cc at wp + 32 cc
-            asm volatile("" : "+r"(rp), "+r"(wp));
-            double2 xn = make_double2(kInf, kInf);                                   // (c1, c2) of lanes 0 / 1 from the warp below
-            if (rd) {
-                const unsigned r0 = rp32 + 32u * (tb0 == 0 ? R : tb0);
-                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xn.x), "=d"(xn.y) : "r"(r0));
-            }
-            uint32_t wt = 0;
-            static_for([&](auto cc_tag) {
-                constexpr int cc = decltype(cc_tag)::value;
-                const double2 x = xn;
-                if (cc + 1 < TT && rd)                     // ahead of this column's ring store
-                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(xn.x), "=d"(xn.y) : "r"(rp), "n"(32 * (cc + 1)));
-                double c1 = __shfl_up_sync(0xFFFFFFFFu, c, 1);
-                if (lane == 0) c1 = x.x;
-                const double oc = acc[cc];
-                uint32_t cd = (uint32_t)BS << (BITS * cc);
-                double minc = __dadd_rn(__dadd_rn(c, oc), 1.0);
-                if (BS == 2) {
-                    double c2 = __shfl_up_sync(0xFFFFFFFFu, c, 2);
-                    if (lane < 2) c2 = x.y;
-                    const double cand = __dadd_rn(__dadd_rn(c2, oc), 2.0);
-                    if (cand < minc) { minc = cand; cd = 0; }
-                }
-                {
-                    const double cand = __dadd_rn(c1, oc);         // transition 0: adding +0.0 is the identity
-                    if (cand < minc) { minc = cand; cd = (uint32_t)(BS - 1) << (BITS * cc); }
-                }
-                if (FULL || cc < ncols) {
-                    c = minc;
-                    wt |= cd;
-                    if (pub) asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(wp), "n"(32 * cc), "d"(c) : "memory");
-                    if (pub31) asm volatile("st.shared.v2.f64 [%0+%1], {%2, %2};" ::"r"(wp), "n"(32 * cc + 16), "d"(c) : "memory");
-                }
-            }, std::make_integer_sequence<int, TT>{});
-            word |= wt << (BITS * TT * (tile % WPT));
-            if ((tile % WPT) == WPT - 1 || tend == T) {
-                bpp[(int64_t)(tile / WPT) * Spad + i] = word;
-                word = 0;
-            }
-            // the tile is consumed and its exit costs are published: the counter serves the warp above as "data
-            // ready" and the warp below as "positions free" (so the last warp counts as well)
-            __syncwarp();
-            if (lane == 0) st_release_shared(done + w, tend);
-        };
-        int t0 = 0, tile = 0;
-        for (; t0 + TT <= T; t0 += TT, ++tile) tile_body(std::true_type{}, t0, tile);
-        if (t0 < T) tile_body(std::false_type{}, t0, tile);
-    }
-    fin[i] = active ? c : kInf;
-    __syncthreads();
-
-    // ---- indmin(costtable[:, T+1]) -- first minimum  (src/dtw.jl:137)
-    {
-        double v = fin[i];
-        int idx = active ? i : 0x7FFFFFFF;
-        if (v != v && i != 0) v = kInf;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            double ov = __shfl_down_sync(0xFFFFFFFFu, v, o);
-            int oi = __shfl_down_sync(0xFFFFFFFFu, idx, o);
-            if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
-        }
-        if (lane == 0) { red_v[w] = v; red_i[w] = idx; }
-        __syncthreads();
-        if (w == 0) {
-            v = (lane < nw) ? red_v[lane] : kInf;
-            idx = (lane < nw) ? red_i[lane] : 0x7FFFFFFF;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                double ov = __shfl_down_sync(0xFFFFFFFFu, v, o);
-                int oi = __shfl_down_sync(0xFFFFFFFFu, idx, o);
-                if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
-            }
-            if (lane == 0) {
-                s_best = idx;
-                if (final_cost) final_cost[p] = v;
-            }
-        }
-        __syncthreads();
-    }
-    // ---- backward  (src/dtw.jl:139-142)
-    if (threadIdx.x < 32) {
-        int st = s_best;
-        int64_t* path = paths + sb;
-        if (lane == 0) path[T - 1] = st + 1;
-        int cur_wi = -1, wbase = 0;
-        uint32_t wd = 0;
-        for (int t = T - 1; t >= 1; --t) {
-            const int wi = t / PER;
-            if (wi != cur_wi || st < wbase || st >= wbase + 32) {
-                wbase = max(0, min(st - 31, Spad - 32));
-                wd = bpp[(int64_t)wi * Spad + wbase + lane];
-                cur_wi = wi;
-            }
-            const uint32_t ww = __shfl_sync(0xFFFFFFFFu, wd, st - wbase);
-            const int code = (int)((ww >> (BITS * (t % PER))) & MASK);
-            st = st + code - BS;
-            if (lane == 0) path[t - 1] = st + 1;
-        }
-    }
-}
-
-template <int BITS, int TT, int REGS, int DT, int BS>
-static int32_t launch_dtw_pipe(const double* tmplT, const int64_t* d_toff, const double* seq, const int64_t* d_soff,
-                               const int64_t* d_bpoff, const int64_t* d_order, uint32_t* bp, int64_t npairs, int maxS, int64_t* paths,
-                               double* final_cost, cudaStream_t st) {
-    const int nt = round_up(maxS, 32), nw = nt / 32;
-    const size_t smem = ((size_t)nw * 4 * (4 * TT + 1) + nt) * sizeof(double) + (size_t)nw * sizeof(int);
-    auto k = dtw_pipe_kernel<BITS, TT, REGS, DT, BS>;
-    VCB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<(unsigned)npairs, nt, smem, st>>>(tmplT, d_toff, seq, d_soff, d_bpoff, d_order, bp, paths, final_cost);
-    count_launch();
-    VCB_CUDA(cudaGetLastError());
-    return VCB_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
-// STREAM kernel: the same warp pipeline as a PERSISTENT kernel -- one CTA per SM walks a list of pairs
-// (balanced on the host by decreasing cost), and a warp that has finished its states' last tile of one
-// pair starts on the next pair at once, so the pipeline fills and drains once per LAUNCH, not once per
-// pair.  Hand-overs are mbarriers (hardware-suspended waits: a polling loop with __nanosleep overslept
-// by microseconds and the delays accumulated down the chain of warps): per warp interface a ring of
-// RT "full" (tile published) and RT "empty" (tile consumed) barriers.  Sequence tiles arrive through a
-// private cp.async double buffer one tile ahead, template values by coalesced (L1-resident) loads one
-// k-step ahead.  The final-minimum search and the back-tracking of pair q run in a SERVICE warp while
-// the compute warps are already in pair q+1 (final costs double-buffered in shared memory).
-// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void dtw_mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -569,7 +344,12 @@ dtw_stream_kernel(const double* __restrict__ tmpl, const int64_t* __restrict__ t
                   double* __restrict__ final_cost) {
     constexpr int PER = 32 / BITS;
     constexpr int RT = 4, R = RT * TT;           // ring: RT tiles of TT columns a warp may run ahead of its consumer
-    constexpr int RS = 4 * (R + 1);              // doubles per warp: positions 1..R of 4 doubles (see dtw_pipe_kernel)
+    // ring[w][pos][4], pos = 1..R: the costs of the warp's last two states ENTERING column t sit at position
+    // ((t' - 1) mod R) + 1 (t' counts the columns of the warp interface over all pairs) as [b1, b0, b1, b1]
+    // (b0: lane 30, b1: lane 31), so that lane 0 of the warp above reads (c1, c2) = (b1, b0) and lane 1 reads
+    // (-, c2) = (b1, b1) with one 16-byte load each; the positions a tile WRITES are contiguous and so are the
+    // ones it READS, except the first.
+    constexpr int RS = 4 * (R + 1);              // doubles per warp: positions 1..R of 4 doubles (position 0 unused)
     constexpr int WPT = PER / TT;                // tiles per back-pointer word
     constexpr uint32_t MASK = (1u << BITS) - 1u;
     constexpr int D = DT;
@@ -701,24 +481,26 @@ dtw_stream_kernel(const double* __restrict__ tmpl, const int64_t* __restrict__ t
 #pragma unroll
             for (int cc = 0; cc < TT; ++cc) acc[cc] = 0.0;
             {
+                // two dimensions at a time, all TT columns side by side: every stage (subtract, square, add) is
+                // TT or 2 TT independent operations, so the FP64 pipe never waits for a dependent result
                 const double2* vb = reinterpret_cast<const double2*>(mytiles + (size_t)(tile & 1) * TT * D);
-                double2 ta = mytmpl[0], tc = mytmpl[32];
+                double2 tk = mytmpl[0];
 #pragma unroll
-                for (int k4 = 0; k4 < D; k4 += 4) {
-                    double2 na = ta, nc = tc;
-                    if (k4 + 4 < D) { na = mytmpl[32 * (k4 / 2 + 2)]; nc = mytmpl[32 * (k4 / 2 + 3)]; }     // a k-step ahead
+                for (int k2 = 0; k2 < D / 2; ++k2) {
+                    double2 tn = tk;
+                    if (k2 + 1 < D / 2) tn = mytmpl[32 * (k2 + 1)];     // a step ahead
+                    double2 v[TT];
 #pragma unroll
-                    for (int cc = 0; cc < TT; ++cc) {       // columns past the sequence: stale tile data, results unused
-                        const double2 va = vb[cc * (D / 2) + k4 / 2], vc = vb[cc * (D / 2) + k4 / 2 + 1];
-                        const double d0 = __dsub_rn(va.x, ta.x), d1 = __dsub_rn(va.y, ta.y);
-                        const double d2 = __dsub_rn(vc.x, tc.x), d3 = __dsub_rn(vc.y, tc.y);
-                        // (0.0 + d0^2 is d0^2: a square is never -0.0)
-                        acc[cc] = k4 == 0 ? __dmul_rn(d0, d0) : __dadd_rn(acc[cc], __dmul_rn(d0, d0));
-                        acc[cc] = __dadd_rn(acc[cc], __dmul_rn(d1, d1));
-                        acc[cc] = __dadd_rn(acc[cc], __dmul_rn(d2, d2));
-                        acc[cc] = __dadd_rn(acc[cc], __dmul_rn(d3, d3));
-                    }
-                    ta = na; tc = nc;
+                    for (int cc = 0; cc < TT; ++cc) v[cc] = vb[cc * (D / 2) + k2];      // columns past the sequence: stale data, unused
+#pragma unroll
+                    for (int cc = 0; cc < TT; ++cc) { v[cc].x = __dsub_rn(v[cc].x, tk.x); v[cc].y = __dsub_rn(v[cc].y, tk.y); }
+#pragma unroll
+                    for (int cc = 0; cc < TT; ++cc) { v[cc].x = __dmul_rn(v[cc].x, v[cc].x); v[cc].y = __dmul_rn(v[cc].y, v[cc].y); }
+#pragma unroll
+                    for (int cc = 0; cc < TT; ++cc) acc[cc] = k2 == 0 ? v[cc].x : __dadd_rn(acc[cc], v[cc].x);   // (0.0 + d^2 is d^2: a square is never -0.0)
+#pragma unroll
+                    for (int cc = 0; cc < TT; ++cc) acc[cc] = __dadd_rn(acc[cc], v[cc].y);
+                    tk = tn;
                 }
             }
             // ---- hand-over, once per tile: the warp below has published the costs entering every column of
@@ -852,17 +634,6 @@ static int32_t launch_dtw(const double* tmplT, const int64_t* d_toff, const doub
 #define VCB_DTW_ARGS tmplT, d_toff, seq, d_soff, d_bpoff, d_order, bp, D, fstep, bstep, npairs, maxS, paths, final_cost, st
     const int nt = round_up(maxS, 32);
     static const int two_ctas = [] { const char* e = getenv("VCB_DTW_2CTA"); return e ? atoi(e) : 1; }();
-    // VCB_DTW_PIPE=1: barrier-free warp pipeline for the reference's own windows (fstep 0, bstep 1 / 2) and
-    // an even compile-time dimension.  Bit-exact, but MEASURED SLOWER than the barrier kernel (C3: 4.41 vs
-    // 2.79 ms): passing the two boundary costs through shared-memory flags costs more per column (~350
-    // cycles: release store, acquire poll, ring read) than one __syncthreads of 21 warps (~100), and the
-    // warps of a CTA still move through observation and recurrence phases together.  Kept as an experiment.
-    static const int pipe = [] { const char* e = getenv("VCB_DTW_PIPE"); return e ? atoi(e) : 0; }();
-    if constexpr (DT > 0 && DT % 4 == 0 && FS == 0 && (BS == 1 || BS == 2) && BITS == 2) {
-        const bool aligned = (reinterpret_cast<uintptr_t>(seq) & 31) == 0;      // 32-byte frame loads
-        if (pipe && aligned && nt <= 672) return launch_dtw_pipe<BITS, 8, 48, DT, BS>(tmplT, d_toff, seq, d_soff, d_bpoff, d_order, bp, npairs, maxS, paths, final_cost, st);
-        if (pipe && aligned && nt <= 1024) return launch_dtw_pipe<BITS, 8, 64, DT, BS>(tmplT, d_toff, seq, d_soff, d_bpoff, d_order, bp, npairs, maxS, paths, final_cost, st);
-    }
     // <= 672 states and a compile-time dimension: two CTAs per SM (8-column tiles, 48 registers): one
     // CTA's barrier-paced recurrence overlaps the other's FP64-bound observation costs (the
     // runtime-dimension build would spill at 48 registers)
@@ -950,9 +721,10 @@ int32_t dtw_fit_batch_device(const double* d_tmpl, const int64_t* h_toff, const 
     VCB_CUDA(cudaMemcpyAsync(d_off + 3 * noff, order.data(), (size_t)npairs * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     int32_t rc;
     // Persistent stream kernel: the reference's own windows, the common dimensions, templates whose warp slices fit
-    // in shared memory (D = 24: up to 672 frames), 16-byte aligned matrices.  VCB_DTW_PIPE=0 keeps the barrier kernel.
-    static const int pipe_mode = [] { const char* e = getenv("VCB_DTW_PIPE"); return e ? atoi(e) : 0; }();
-    if (pipe_mode == 2 && fstep == 0 && (bstep == 1 || bstep == 2) && (D == 24 || D == 40) && dtw_stream_fits(maxS, D, 8) &&
+    // in shared memory (D = 24: up to 672 frames), 16-byte aligned matrices.  VCB_DTW_STREAM=0 or
+    // vcb_set_kernel_variant(1) keep the barrier kernel (cross-check in the tests).
+    static const int stream_on = [] { const char* e = getenv("VCB_DTW_STREAM"); return e ? atoi(e) : 1; }();
+    if (stream_on && g_variant.load() != 1 && fstep == 0 && (bstep == 1 || bstep == 2) && (D == 24 || D == 40) && dtw_stream_fits(maxS, D, 8) &&
         ((reinterpret_cast<uintptr_t>(d_seq) | reinterpret_cast<uintptr_t>(d_tmpl)) & 15) == 0) {
         int dev = 0, nsm = 0;
         VCB_CUDA(cudaGetDevice(&dev));
