@@ -34,7 +34,11 @@ elif which == "gv":
     ms = timeit(lambda: vcb.vc_batch(tg, d, off, _split=False, epochs=ep))
     print(f"traj+GV C2 n={n} limit={limit} epochs={ep}: {ms:.3f} ms  {n*500/ms*1e3:.3e} frames/s")
 elif which == "dtw":
-    tm, to, sq, so = vcb.synth.config_c3(int(os.environ.get("N_PAIRS", 1000)))
+    if "S_RANGE" in os.environ:      # e.g. S_RANGE=640,640: every template / sequence length in that range
+        lo, hi = (int(x) for x in os.environ["S_RANGE"].split(","))
+        tm, to, sq, so = vcb.synth.dtw_pairs(int(os.environ.get("N_PAIRS", 1000)), 24, (lo, hi), 1003)
+    else:
+        tm, to, sq, so = vcb.synth.config_c3(int(os.environ.get("N_PAIRS", 1000)))
     a = torch.from_numpy(np.ascontiguousarray(tm.T)).cuda(); b = torch.from_numpy(np.ascontiguousarray(sq.T)).cuda()
     d = vcb.DTWs.DTW(fstep=0, bstep=2)
     ms = timeit(lambda: vcb.DTWs.fit_batch(d, a, to, b, so))
