@@ -67,7 +67,7 @@ def config_for(path: str, world: int) -> dict:
                                "optional NCCL gather timed separately"}
     return {"workload": "C3: DTW(fstep=0, bstep=2) of 1000 parallel utterance pairs (~600x600 frames, 24-dim) per GPU",
             "pairs_per_gpu": 1000, "dim": 24, "fstep": 0, "bstep": 2,
-            "l2": "the fused kernel keeps the cost column on chip; templates + sequences + back-pointers = 0.3 GB per step",
+            "l2": "the kernel keeps the cost column in registers; templates + sequences + back-pointers = 0.3 GB per step, larger than the 126 MB L2",
             "parallelism": f"pairs sharded over {world} GPU(s), no data-path collective"}
 
 
@@ -639,15 +639,15 @@ def run_dtw(ctx: Ctx, steps: int, warmup: int) -> dict:
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                      "traffic": prof["traffic"], "traffic_unit": "bytes/launch (DRAM read+write, ncu)",
-                     "traffic_source": prof["source"], "kernel": "dtw_fused_kernel", "kernel_ms": kms,
+                     "traffic_source": prof["source"], "kernel": "dtw_stream_kernel", "kernel_ms": kms,
                      "algorithmic_bytes_per_cell": B_DTW, "cells_per_launch": cells,
                      "peak_source": f"HBM copy bandwidth {ctx.peak_src}",
                      "fp64_pipe": {"dp_ops_per_cell": DP_OPS_PER_CELL, "floor_ms": fp64_floor_ms, "frac_of_floor": fp64_floor_ms / kms,
                                    "ncu_pipe_fp64_active_pct": prof.get("sm__pipe_fp64_cycles_active"),
                                    "note": "64 FP64 lanes/clk/SM x 148 SMs at the maximum SM clock"},
                      "note": "achieved uses SURVEY 8d's 17 B/cell of the two-pass form (cost matrix written + read, 1 B "
-                             "back-pointer); the kernel is fused (cost matrix never leaves the SM), so the real bound "
-                             "is the FP64 pipe: see fp64_pipe"},
+                             "back-pointer); the kernel is fused (persistent warp pipeline, cost matrix never leaves the "
+                             "SM), so the real bound is the FP64 pipe: see fp64_pipe"},
     }
 
 

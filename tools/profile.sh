@@ -17,5 +17,6 @@ cap prof_traj     traj_solve_warp      1 python tools/run_path.py traj 1
 cap prof_argmax   gmm_tc_kernel        1 python tools/run_path.py traj 1
 cap prof_group    group_panel          1 python tools/run_path.py traj 1
 cap prof_recheck  recheck_panel_kernel 1 python tools/run_path.py traj 1
-cap prof_dtw      dtw_fused_kernel     1 python tools/run_path.py dtw 1
+cap prof_dtw      dtw_stream_kernel    1 python tools/run_path.py dtw 1
+cap prof_dtwbarrier dtw_fused_kernel   1 env VCB_DTW_STREAM=0 python tools/run_path.py dtw 1
 ls -la gpurun_out | grep _$R
