@@ -613,9 +613,10 @@ def run_dtw(ctx: Ctx, steps: int, warmup: int) -> dict:
     # end to end: host arrays through vcb_dtw_fit_batch
     _, htm = ctx.pinned(tm.T)
     _, hsq = ctx.pinned(sq.T)
-    vcb.DTWs.fit_batch(d, htm, to, hsq, so)
+    for _ in range(3):          # the first calls grow the stream-ordered pool and the page-locked bounce buffer
+        vcb.DTWs.fit_batch(d, htm, to, hsq, so)
     ctx.barrier()
-    e2e_steps = 5
+    e2e_steps = 10
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         hp, hc = vcb.DTWs.fit_batch(d, htm, to, hsq, so)
