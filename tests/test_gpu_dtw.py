@@ -70,8 +70,8 @@ def test_ragged_and_tiny_compile_time_dimension(vcb, oracle):
             paths, fc = vcb.DTWs.fit_batch(vcb.DTWs.DTW(fstep=fs, bstep=bs), tm, to, sq, so)
             ref, rfc = oracle.dtw_fit_batch(tm, to, sq, so, fs, bs)
             assert np.array_equal(paths, ref) and np.array_equal(fc, rfc), (D, fs, bs)
-        # templates of up to 672 / 97 frames only: the batch maximum decides the kernel and the CTA width
-        # (D = 24: 21 + 1 warps of the stream kernel; a few warps)
+        # templates of up to 672 / 97 frames only: the longest template decides the CTA width of the stream kernel
+        # (D = 24: 21 + 1 warps; a few warps); in the full batch above it shares the launch with the barrier kernel
         for smax in (672, 97):
           sel = [i for i in range(len(S)) if S[i] <= smax]
           to2 = np.concatenate([[0], np.cumsum([S[i] for i in sel])]); so2 = np.concatenate([[0], np.cumsum([T[i] for i in sel])])

@@ -13,4 +13,4 @@ d = vcb.DTWs.DTW(fstep=0, bstep=2)
 ts = []
 for _ in range(12):
     t0 = time.perf_counter(); vcb.DTWs.fit_batch(d, htm, to, hsq, so); ts.append((time.perf_counter() - t0) * 1e3)
-print("stream=%s slice=%s: " % (os.environ.get("VCB_DTW_STREAM", "1"), os.environ.get("VCB_DTW_SLICE", "296")) + " ".join(f"{t:.2f}" for t in ts))
+print("stream=%s slice=%s: " % (os.environ.get("VCB_DTW_STREAM", "1"), os.environ.get("VCB_DTW_SLICE", "148")) + " ".join(f"{t:.2f}" for t in ts))

@@ -689,27 +689,43 @@ int32_t dtw_fit_batch_device(const double* d_tmpl, const int64_t* h_toff, const 
     if (window > 256) return fail(VCB_EUNSUPPORTED, "DTW window fstep+bstep+1 = %d > 256", window);
     const int bits = window <= 4 ? 2 : (window <= 16 ? 4 : 8);
     const int per = 32 / bits;
-    int maxS = 0;
     std::vector<int64_t> bpoff(npairs + 1, 0);
     for (int64_t p = 0; p < npairs; ++p) {
         const int64_t S = h_toff[p + 1] - h_toff[p], T = h_soff[p + 1] - h_soff[p];
         if (S < 1 || T < 1) return fail(VCB_EARG, "pair %lld has an empty template or sequence", (long long)p);
         if (S > kDtwMaxStates)
             return fail(VCB_EUNSUPPORTED, "template of %lld frames: one CTA holds the cost column of up to %d states", (long long)S, kDtwMaxStates);
-        maxS = (int)std::max<int64_t>(maxS, S);
         bpoff[p + 1] = bpoff[p] + ((T + per - 1) / per) * ((S + 31) / 32 * 32);
     }
-    // launch order: decreasing cost S*T, so the short pairs fill the tail of the last wave
-    std::vector<int64_t> order(npairs);
+    // Two kernels share a batch.  The persistent stream kernel takes the pairs it is built for: the reference's own
+    // windows, the common dimensions, templates whose warp slices fit in shared memory (D = 24: up to 672 frames,
+    // D = 40: 416), 16-byte aligned matrices; the barrier kernel takes the rest (VCB_DTW_STREAM=0 or
+    // vcb_set_kernel_variant(1): everything -- the cross-check of the tests).  Inside each group the launch order is
+    // decreasing cost S*T, so the short pairs fill the tail.
+    static const int stream_on = [] { const char* e = getenv("VCB_DTW_STREAM"); return e ? atoi(e) : 1; }();
+    int stream_maxS = 0;
+    if (stream_on && g_variant.load() != 1 && fstep == 0 && (bstep == 1 || bstep == 2) && (D == 24 || D == 40) &&
+        ((reinterpret_cast<uintptr_t>(d_seq) | reinterpret_cast<uintptr_t>(d_tmpl)) & 15) == 0)
+        while (dtw_stream_fits(stream_maxS + 32, D, 8)) stream_maxS += 32;
+    auto cost = [&](int64_t p) { return (h_toff[p + 1] - h_toff[p]) * (h_soff[p + 1] - h_soff[p]); };
+    std::vector<int64_t> order(npairs);          // [pairs of the barrier kernel | pairs of the stream kernel]
     for (int64_t p = 0; p < npairs; ++p) order[p] = p;
-    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
-        return (h_toff[a + 1] - h_toff[a]) * (h_soff[a + 1] - h_soff[a]) > (h_toff[b + 1] - h_toff[b]) * (h_soff[b + 1] - h_soff[b]);
-    });
+    const int64_t nlong = std::stable_partition(order.begin(), order.end(), [&](int64_t p) { return h_toff[p + 1] - h_toff[p] > stream_maxS; }) - order.begin();
+    std::stable_sort(order.begin(), order.begin() + nlong, [&](int64_t x, int64_t y) { return cost(x) > cost(y); });
+    std::stable_sort(order.begin() + nlong, order.end(), [&](int64_t x, int64_t y) { return cost(x) > cost(y); });
+    const int64_t nshort = npairs - nlong;
+    int maxS_long = 0, maxS_short = 0;
+    for (int64_t e = 0; e < npairs; ++e) {
+        const int S = (int)(h_toff[order[e] + 1] - h_toff[order[e]]);
+        if (e < nlong) maxS_long = std::max(maxS_long, S);
+        else maxS_short = std::max(maxS_short, S);
+    }
     const int64_t totalS = h_toff[npairs];
     // scratch: offsets, transposed templates, packed back-pointers (stream-ordered allocation)
     int64_t* d_off = nullptr;
     double* d_tmplT = nullptr;
     uint32_t* d_bp = nullptr;
+    int32_t* d_lists = nullptr;
     const size_t noff = (size_t)(npairs + 1);
     VCB_CUDA(cudaMallocAsync((void**)&d_off, 4 * noff * sizeof(int64_t), st));
     VCB_CUDA(cudaMallocAsync((void**)&d_bp, (size_t)std::max<int64_t>(bpoff[npairs], 1) * sizeof(uint32_t), st));
@@ -719,56 +735,47 @@ int32_t dtw_fit_batch_device(const double* d_tmpl, const int64_t* h_toff, const 
     VCB_CUDA(cudaMemcpyAsync(d_off + noff, h_soff, noff * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     VCB_CUDA(cudaMemcpyAsync(d_off + 2 * noff, bpoff.data(), noff * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     VCB_CUDA(cudaMemcpyAsync(d_off + 3 * noff, order.data(), (size_t)npairs * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    int32_t rc;
-    // Persistent stream kernel: the reference's own windows, the common dimensions, templates whose warp slices fit
-    // in shared memory (D = 24: up to 672 frames), 16-byte aligned matrices.  VCB_DTW_STREAM=0 or
-    // vcb_set_kernel_variant(1) keep the barrier kernel (cross-check in the tests).
-    static const int stream_on = [] { const char* e = getenv("VCB_DTW_STREAM"); return e ? atoi(e) : 1; }();
-    if (stream_on && g_variant.load() != 1 && fstep == 0 && (bstep == 1 || bstep == 2) && (D == 24 || D == 40) && dtw_stream_fits(maxS, D, 8) &&
-        ((reinterpret_cast<uintptr_t>(d_seq) | reinterpret_cast<uintptr_t>(d_tmpl)) & 15) == 0) {
+    int32_t rc = VCB_OK;
+    stage_begin(st);
+    if (nlong > 0) {
+        VCB_CUDA(cudaMallocAsync((void**)&d_tmplT, (size_t)totalS * D * sizeof(double), st));
+        dim3 grid((unsigned)npairs, (maxS_long + 31) / 32), block(32, 8);      // (short pairs are transposed along: 3 % of a step)
+        dtw_transpose_kernel<<<grid, block, 0, st>>>(d_tmpl, d_off, d_tmplT, D);
+        count_launch();
+        VCB_CUDA(cudaGetLastError());
+    }
+    stage_mark(st);      // [0] template transpose (barrier kernel only); [1] the DTW kernels
+    if (nshort > 0) {
         int dev = 0, nsm = 0;
         VCB_CUDA(cudaGetDevice(&dev));
         VCB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-        const int nb = (int)std::min<int64_t>(npairs, nsm);
+        const int nb = (int)std::min<int64_t>(nshort, nsm);
         std::vector<int32_t> first, list;
-        dtw_balance(order, h_toff, h_soff, nb, first, list);
-        int32_t* d_lists = nullptr;
-        VCB_CUDA(cudaMallocAsync((void**)&d_lists, (size_t)(nb + 1 + npairs) * sizeof(int32_t), st));
+        dtw_balance(std::vector<int64_t>(order.begin() + nlong, order.end()), h_toff, h_soff, nb, first, list);
+        VCB_CUDA(cudaMallocAsync((void**)&d_lists, (size_t)(nb + 1 + nshort) * sizeof(int32_t), st));
         VCB_CUDA(cudaMemcpyAsync(d_lists, first.data(), (size_t)(nb + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        VCB_CUDA(cudaMemcpyAsync(d_lists + nb + 1, list.data(), (size_t)npairs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        stage_begin(st);
-        stage_mark(st);      // [0] (no template transpose on this path); [1] the stream kernel
-#define VCB_DTW_STREAM(MAXT, DT, BS) launch_dtw_stream<2, 8, MAXT, DT, BS>(d_tmpl, d_off, d_seq, d_off + noff, d_off + 2 * noff, d_lists, d_lists + nb + 1, nb, d_bp, maxS, d_paths, d_final_cost, st)
+        VCB_CUDA(cudaMemcpyAsync(d_lists + nb + 1, list.data(), (size_t)nshort * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+#define VCB_DTW_STREAM(MAXT, DT, BS) launch_dtw_stream<2, 8, MAXT, DT, BS>(d_tmpl, d_off, d_seq, d_off + noff, d_off + 2 * noff, d_lists, d_lists + nb + 1, nb, d_bp, maxS_short, d_paths, d_final_cost, st)
         // at most 21 compute warps + the service warp fit (shared memory): 704 threads, 80 registers each
         if (D == 24 && bstep == 2) rc = VCB_DTW_STREAM(704, 24, 2);
         else if (D == 24) rc = VCB_DTW_STREAM(704, 24, 1);
         else if (bstep == 2) rc = VCB_DTW_STREAM(704, 40, 2);
         else rc = VCB_DTW_STREAM(704, 40, 1);
 #undef VCB_DTW_STREAM
-        stage_mark(st);
-        cudaFreeAsync(d_lists, st);
-        cudaFreeAsync(d_off, st);
-        cudaFreeAsync(d_bp, st);
-        return rc;
     }
-    VCB_CUDA(cudaMallocAsync((void**)&d_tmplT, (size_t)totalS * D * sizeof(double), st));
-    stage_begin(st);
-    {
-        dim3 grid((unsigned)npairs, (maxS + 31) / 32), block(32, 8);
-        dtw_transpose_kernel<<<grid, block, 0, st>>>(d_tmpl, d_off, d_tmplT, D);
-        count_launch();
-        VCB_CUDA(cudaGetLastError());
+    if (nlong > 0 && rc == VCB_OK) {
+#define VCB_DTW_CALL d_tmplT, d_off, d_seq, d_off + noff, d_off + 2 * noff, d_off + 3 * noff, d_bp, D, fstep, bstep, nlong, maxS_long, d_paths, d_final_cost, st
+        if (fstep == 0 && bstep == 1) rc = launch_dtw_dim<2, 1, 0>(VCB_DTW_CALL);
+        else if (fstep == 0 && bstep == 2) rc = launch_dtw_dim<2, 2, 0>(VCB_DTW_CALL);
+        else if (bits == 2) rc = launch_dtw_dim<2, -1, 0>(VCB_DTW_CALL);
+        else if (bits == 4) rc = launch_dtw_dim<4, -1, 0>(VCB_DTW_CALL);
+        else rc = launch_dtw_dim<8, -1, 0>(VCB_DTW_CALL);
+#undef VCB_DTW_CALL
     }
-    stage_mark(st);      // [0] template transpose; [1] the fused kernel
-#define VCB_DTW_CALL d_tmplT, d_off, d_seq, d_off + noff, d_off + 2 * noff, d_off + 3 * noff, d_bp, D, fstep, bstep, npairs, maxS, d_paths, d_final_cost, st
-    if (fstep == 0 && bstep == 1) rc = launch_dtw_dim<2, 1, 0>(VCB_DTW_CALL);
-    else if (fstep == 0 && bstep == 2) rc = launch_dtw_dim<2, 2, 0>(VCB_DTW_CALL);
-    else if (bits == 2) rc = launch_dtw_dim<2, -1, 0>(VCB_DTW_CALL);
-    else if (bits == 4) rc = launch_dtw_dim<4, -1, 0>(VCB_DTW_CALL);
-    else rc = launch_dtw_dim<8, -1, 0>(VCB_DTW_CALL);
     stage_mark(st);
+    if (d_lists) cudaFreeAsync(d_lists, st);
     cudaFreeAsync(d_off, st);
-    cudaFreeAsync(d_tmplT, st);
+    if (d_tmplT) cudaFreeAsync(d_tmplT, st);
     cudaFreeAsync(d_bp, st);
     return rc;
 }
