@@ -1,7 +1,7 @@
 #!/bin/bash
 # End-of-session evidence run on the GPU box (repo root): full GPU parity suite, the three bench lines,
 # launch list + ncu captures of the DTW kernels, compute-sanitizer on the DTW tests.  Outputs: gpurun_out/.
-R=${1:-r02c}
+R=${1:-r02d}
 mkdir -p gpurun_out
 S=gpurun_out/final_$R.log
 : > $S
