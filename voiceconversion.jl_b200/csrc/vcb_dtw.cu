@@ -645,16 +645,7 @@ static int32_t launch_dtw(const double* tmplT, const int64_t* d_toff, const doub
     // CTA's barrier-paced recurrence overlaps the other's FP64-bound observation costs (the
     // runtime-dimension build would spill at 48 registers)
     if (nt <= 672 && two_ctas && DT > 0) {
-        // experiment switch: states per thread / tile width / CTAs per SM for the common shape
-        static const int cfg = [] { const char* e = getenv("VCB_DTW_CFG"); return e ? atoi(e) : 0; }();
-        if constexpr (DT == 24 && BS == 2) {
-            if (cfg == 1 && maxS <= 704) return launch_dtw_cfg<BITS, 8, 352, 3, DT, BS, FS, 2>(VCB_DTW_ARGS);
-            if (cfg == 2 && maxS <= 704) return launch_dtw_cfg<BITS, 4, 352, 4, DT, BS, FS, 2>(VCB_DTW_ARGS);
-            if (cfg == 3 && maxS <= 704) return launch_dtw_cfg<BITS, 8, 352, 4, DT, BS, FS, 2>(VCB_DTW_ARGS);
-            if (cfg == 5 && maxS <= 704) return launch_dtw_cfg<BITS, 16, 352, 2, DT, BS, FS, 2>(VCB_DTW_ARGS);
-            if (cfg == 6 && maxS <= 704) return launch_dtw_cfg<BITS, 4, 192, 6, DT, BS, FS, 4>(VCB_DTW_ARGS);
-            if (cfg == 7 && maxS <= 704) return launch_dtw_cfg<BITS, 8, 192, 4, DT, BS, FS, 4>(VCB_DTW_ARGS);
-        }
+        // (two states per thread with 3-4 CTAs/SM measured 3.1-7.6 ms against 2.78: profiles/r02_experiments.txt)
         return launch_dtw_cfg<BITS, 8, 672, 2, DT, BS, FS, 1>(VCB_DTW_ARGS);
     }
     // <= 768 states: 16-column tiles (80-register budget); up to 1024: 8-column tiles
