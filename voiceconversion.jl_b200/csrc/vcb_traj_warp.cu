@@ -48,13 +48,14 @@ __device__ __forceinline__ double2 tile_transpose(const double2 x, int r, int q)
     return (r & 1) ? make_double2(a1, b1) : make_double2(a0, b0);
 }
 
-// 1/sqrt(d) to about one ulp from the fp32 approximation and one third-order correction
-// (e = 1 - d y^2,  y += y e (1/2 + 3/8 e)): 8 instructions and a 70-cycle chain instead of the
-// library's 14 / 110 -- this sits 24 times per frame on the serial chain of the factorisation.
+// 1/sqrt(d) to about one ulp from the hardware's 20-bit approximation (rsqrt.approx.f64 = MUFU.RSQ64H, one instruction
+// on the high word -- the fp32 route costs two conversions more on the serial chain) and one third-order correction
+// (e = 1 - d y^2,  y += y e (1/2 + 3/8 e); |e| < 2^-19, so the remainder 5/16 e^3 is below 2^-58): 6 instructions and a
+// ~55-cycle chain instead of the library's 14 / 110 -- this sits 24 times per frame on the serial chain of the
+// factorisation.
 __device__ __forceinline__ double fast_rsqrt(double d) {
-    float y0;                                                   // (the caller flags pivots outside the fp32 range)
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(__double2float_rn(d)));
-    const double y = (double)y0;
+    double y;                                                   // (the caller flags pivots outside 2^-100 .. 2^100)
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
     const double t = d * y;
     const double e = fma(-t, y, 1.0);
     const double c = fma(0.375, e, 0.5);
