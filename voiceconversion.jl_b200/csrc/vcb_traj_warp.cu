@@ -48,6 +48,14 @@ __device__ __forceinline__ double2 tile_transpose(const double2 x, int r, int q)
     return (r & 1) ? make_double2(a1, b1) : make_double2(a0, b0);
 }
 
+// 2^-100 <= d < 2^100, tested on the exponent field with integer compares (negative numbers, NaN and infinities fall
+// outside as unsigned values): the check feeds only the error flag and should not take FP64-pipe slots next to the
+// factorisation's serial chain.
+__device__ __forceinline__ bool sane_pivot(double d) {
+    const unsigned hi = (unsigned)__double2hiint(d);
+    return hi - 0x39B00000u < 0x46300000u - 0x39B00000u;          // biased exponents 1023 - 100 .. 1023 + 99
+}
+
 // 1/sqrt(d) to about one ulp from the hardware's 20-bit approximation (rsqrt.approx.f64 = MUFU.RSQ64H, one instruction
 // on the high word -- the fp32 route costs two conversions more on the serial chain) and one third-order correction
 // (e = 1 - d y^2,  y += y e (1/2 + 3/8 e); |e| < 2^-19, so the remainder 5/16 e^3 is below 2^-58): 6 instructions and a
@@ -78,7 +86,7 @@ __device__ __forceinline__ double2 diag_inverse(const double2 d, int lane, int r
         const int qc = c >> 1;
         const double mine = (c & 1) ? a.y : a.x;                   // a[r][c] in the lanes with q == qc
         const double piv = __shfl_sync(kFull, mine, 4 * c + qc);
-        bad |= !(piv > 0x1p-100 && piv < 0x1p100);                  // not positive (or not a sane pivot at all)
+        bad |= !sane_pivot(piv);                                    // not positive (or not a sane pivot at all)
         const double di = fast_rsqrt(piv);
         const double lcol = mine * di;                              // l[r][c], rows >= c, lanes q == qc
         const double lr = __shfl_sync(kFull, lcol, (lane & ~3) | qc);
@@ -124,7 +132,7 @@ __device__ __forceinline__ double2 diag_inverse_redundant(const double2 d, doubl
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         const double dd = a[c][c];
-        bad |= !(dd > 0x1p-100 && dd < 0x1p100);       // not positive (or not a sane pivot at all)
+        bad |= !sane_pivot(dd);                        // not positive (or not a sane pivot at all)
         di[c] = fast_rsqrt(dd);
 #pragma unroll
         for (int i = c + 1; i < 8; ++i) a[i][c] *= di[c];
