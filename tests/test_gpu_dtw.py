@@ -82,6 +82,22 @@ def test_ragged_and_tiny_compile_time_dimension(vcb, oracle):
             assert np.array_equal(paths, ref) and np.array_equal(fc, rfc), (D, smax, bs)
 
 
+@pytest.mark.parametrize("bstep", [2, 1])
+def test_many_pairs_per_persistent_cta(vcb, oracle, bstep):
+    """More pairs than SMs, template lengths from 1 to 672 and sequence lengths from 1 to 150 in random order: every
+    persistent CTA of the stream kernel walks several pairs whose numbers of active warps differ (a warp's tile counters
+    towards its neighbours, the ring stages and the service warp's double buffer all carry over from pair to pair)."""
+    rng = np.random.default_rng(31 + bstep)
+    n = 700
+    S = rng.integers(1, 673, size=n); T = rng.integers(1, 151, size=n)
+    S[:8] = [672, 1, 641, 32, 640, 33, 31, 671]; T[:8] = [150, 1, 8, 9, 7, 16, 149, 1]
+    to = np.concatenate([[0], np.cumsum(S)]).astype(np.int64); so = np.concatenate([[0], np.cumsum(T)]).astype(np.int64)
+    tm = np.asfortranarray(rng.standard_normal((24, to[-1]))); sq = np.asfortranarray(rng.standard_normal((24, so[-1])))
+    paths, fc = vcb.DTWs.fit_batch(vcb.DTWs.DTW(fstep=0, bstep=bstep), tm, to, sq, so)
+    ref, rfc = oracle.dtw_fit_batch(tm, to, sq, so, 0, bstep, nthreads=oracle.max_threads())
+    assert np.array_equal(paths, ref) and np.array_equal(fc, rfc)
+
+
 @pytest.mark.parametrize("S,T", [(1025, 40), (1500, 300), (2500, 120), (4097, 33), (8192, 17)])
 def test_long_templates_bit_exact(vcb, oracle, S, T):
     """Templates beyond 1024 frames (5.1 s at the reference's 5 ms shift): the reference has no
