@@ -167,7 +167,8 @@ def device_count() -> int:
 
 
 def set_kernel_variant(variant: int) -> None:
-    """0 = auto, 1 = CUDA-core fp32 kernel, 2 = tcgen05 3xTF32 kernel (tests / profiling)."""
+    """0 = auto, 1 = CUDA-core fp32 posterior kernel (and the per-column barrier DTW kernel instead of the
+    persistent warp-pipeline one), 2 = tcgen05 3xTF32 kernel (tests / profiling)."""
     check(lib().vcb_set_kernel_variant(variant))
 
 
