@@ -19,7 +19,11 @@ def timeit(fn):
 if which == "traj":
     n = int(os.environ.get("N_UTT", 1000)); limit = int(os.environ.get("LIMIT", 500))
     M = int(os.environ.get("MIX", 64))
-    gm, fm, off = vcb.synth.config_c2(n, 500, M=M) if M != 64 else vcb.synth.config_c2(n, 500)
+    if "DS" in os.environ:       # other static dimensions (e.g. DS=40: the order-40 fixture shape, 64-thread CTA solver)
+        gm = vcb.synth.random_joint_gmm(1002, M, 4 * int(os.environ["DS"]))
+        fm, off = vcb.synth.trajectory_utterances(gm, n, 500, 1002)
+    else:
+        gm, fm, off = vcb.synth.config_c2(n, 500, M=M) if M != 64 else vcb.synth.config_c2(n, 500)
     t = vcb.TrajectoryGMMMap(vcb.GMMMap(*gm), limit)
     d = torch.from_numpy(np.ascontiguousarray(fm.T)).cuda()
     ms = timeit(lambda: vcb.vc_batch(t, d, off, _split=False))

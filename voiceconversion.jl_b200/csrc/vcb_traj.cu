@@ -275,8 +275,8 @@ traj_solve_tiled(const TrajParams p) {
 #pragma unroll
                 for (int c = 0; c < TS; ++c) {
                     const double d = s[c][c];
-                    if (!(d > 0.0)) atomicExch(p.err, 1);
-                    di[c] = rsqrt(d);
+                    if (!sane_pivot(d)) atomicExch(p.err, 1);        // not positive (or not a sane pivot at all), as in the warp solver
+                    di[c] = fast_rsqrt(d);
                     s[c][c] = d * di[c];
 #pragma unroll
                     for (int r = c + 1; r < TS; ++r) s[r][c] *= di[c];
