@@ -93,17 +93,53 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // Fragment layout: A a0 = X[8*i8 + lane/4][k + lane%4], B b0 = Y[8*j8 + lane/4][k + lane%4],
 // C c0,c1 = [8*i8 + lane/4][8*j8 + 2*(lane%4) + {0,1}].  One warp instruction performs 256 FMAs,
 // so the block products cost ~8x fewer issue slots than per-thread DFMA tiles.
-__device__ __forceinline__ void dmma_tile(double& c0, double& c1, const double* __restrict__ XT,
-                                          const double* __restrict__ YT, int i8, int j8, int kmax,
-                                          int LD, int lane) {
+//
+// NI output tiles of one block column j8 (rows 8 * i8[e]) at once: the B fragment is loaded once per k-step and the
+// NI accumulator chains are independent, so neither the shared-memory latency nor the 26-cycle DMMA latency of a
+// single dependent chain is exposed (dmma_tile, one tile at a time, spent 56 cycles per k-step on both).
+template <int NI>
+__device__ __forceinline__ void dmma_col(double (&c)[3][2], const double* __restrict__ XT, const double* __restrict__ YT,
+                                         const int (&i8)[3], int j8, int kmax, int LD, int lane) {
     const int r = lane >> 2, q = lane & 3;
-    const double* xa = XT + q * LD + i8 * 8 + r;
     const double* yb = YT + q * LD + j8 * 8 + r;
+    const double* xa[NI];
+#pragma unroll
+    for (int e = 0; e < NI; ++e) xa[e] = XT + q * LD + i8[e] * 8 + r;
 #pragma unroll 2
     for (int k = 0; k < kmax; k += 4) {
-        const double a = xa[k * LD], b = yb[k * LD];
-        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                     : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+        const double b = yb[k * LD];
+        double a[NI];
+#pragma unroll
+        for (int e = 0; e < NI; ++e) a[e] = xa[e][k * LD];
+#pragma unroll
+        for (int e = 0; e < NI; ++e)
+            asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                : "+d"(c[e][0]), "+d"(c[e][1]) : "d"(a[e]), "d"(b));
+    }
+}
+
+// acc = X Y' (+ X2 Y2') over the TS x TS output tiles, dealt to the two warps by (i8 + j8) parity so that a warp owns
+// two or three tiles of every block column; tri: Y is lower triangular (k < 8 (j8 + 1)); store(i8, j8, c0, c1).
+template <int TS, class Store>
+__device__ __forceinline__ void block_product(const double* XT, const double* YT, const double* XT2, const double* YT2, bool tri,
+                                              bool enable, int warp, int lane, int LD, Store store) {
+    for (int j8 = 0; j8 < TS; ++j8) {
+        const int ib = (j8 + warp) & 1, ni = (TS - ib + 1) / 2, kmax = tri ? 8 * (j8 + 1) : 8 * TS;
+        const int i8[3] = {ib, ib + 2, ib + 4};
+        double c[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+        if (enable) {
+            if (ni == 3) {
+                dmma_col<3>(c, XT, YT, i8, j8, kmax, LD, lane);
+                if (XT2) dmma_col<3>(c, XT2, YT2, i8, j8, kmax, LD, lane);
+            } else if (ni == 2) {
+                dmma_col<2>(c, XT, YT, i8, j8, kmax, LD, lane);
+                if (XT2) dmma_col<2>(c, XT2, YT2, i8, j8, kmax, LD, lane);
+            } else if (ni == 1) {
+                dmma_col<1>(c, XT, YT, i8, j8, kmax, LD, lane);
+                if (XT2) dmma_col<1>(c, XT2, YT2, i8, j8, kmax, LD, lane);
+            }
+        }
+        for (int e = 0; e < ni; ++e) store(i8[e], j8, c[e][0], c[e][1]);
     }
 }
 
@@ -206,13 +242,10 @@ traj_solve_tiled(const TrajParams p) {
         // to the two warps; fragment element (row, col pair) of this lane inside a tile:
         const int fr = lane >> 2, fc = 2 * (lane & 3);
         // ---- 1. G2 = L[t][t-2] = R[t][t-2] * Linv_{t-2}'   (Linv lower triangular: k < 8*(j8+1))
-        for (int tau = warp; tau < TS * TS; tau += 2) {
-            const int i8 = tau / TS, j8 = tau - i8 * TS;
-            double c0 = 0.0, c1 = 0.0;
-            if (t >= 2) dmma_tile(c0, c1, W, Lm2inv, i8, j8, 8 * (j8 + 1), LD, lane);
+        block_product<TS>(W, Lm2inv, nullptr, nullptr, true, t >= 2, warp, lane, LD, [&](int i8, int j8, double c0, double c1) {
             G2[(8 * j8 + fc) * LD + 8 * i8 + fr] = c0;
             G2[(8 * j8 + fc + 1) * LD + 8 * i8 + fr] = c1;
-        }
+        });
         __syncthreads();
         // ---- 2. Tm = R[t][t-1] - G2 * L[t-1][t-2]'  (into the W buffer; R[t][t-2] is dead)
 #pragma unroll
@@ -221,35 +254,25 @@ traj_solve_tiled(const TrajParams p) {
             for (int x = 0; x < TS; ++x) W[(j0 + y) * LD + i0 + x] = r1[x][y];
         __syncthreads();
         if (t >= 2) {
-            for (int tau = warp; tau < TS * TS; tau += 2) {
-                const int i8 = tau / TS, j8 = tau - i8 * TS;
-                double c0 = 0.0, c1 = 0.0;
-                dmma_tile(c0, c1, G2, Lt1t2, i8, j8, DSP, LD, lane);
+            block_product<TS>(G2, Lt1t2, nullptr, nullptr, false, true, warp, lane, LD, [&](int i8, int j8, double c0, double c1) {
                 W[(8 * j8 + fc) * LD + 8 * i8 + fr] -= c0;
                 W[(8 * j8 + fc + 1) * LD + 8 * i8 + fr] -= c1;
-            }
+            });
         }
         __syncthreads();
         // ---- 3. G1 = L[t][t-1] = Tm * Linv_{t-1}'
-        for (int tau = warp; tau < TS * TS; tau += 2) {
-            const int i8 = tau / TS, j8 = tau - i8 * TS;
-            double c0 = 0.0, c1 = 0.0;
-            if (t >= 1) dmma_tile(c0, c1, W, Lm1inv, i8, j8, 8 * (j8 + 1), LD, lane);
+        block_product<TS>(W, Lm1inv, nullptr, nullptr, true, t >= 1, warp, lane, LD, [&](int i8, int j8, double c0, double c1) {
             G1[(8 * j8 + fc) * LD + 8 * i8 + fr] = c0;
             G1[(8 * j8 + fc + 1) * LD + 8 * i8 + fr] = c1;
-        }
+        });
         __syncthreads();
         // ---- 4. S = R[t][t] - G2 G2' - G1 G1'  (products into the W buffer -- Tm is dead -- then
         //         every thread subtracts its own register tile)
         if (t >= 1) {
-            for (int tau = warp; tau < TS * TS; tau += 2) {
-                const int i8 = tau / TS, j8 = tau - i8 * TS;
-                double c0 = 0.0, c1 = 0.0;
-                dmma_tile(c0, c1, G1, G1, i8, j8, DSP, LD, lane);
-                if (t >= 2) dmma_tile(c0, c1, G2, G2, i8, j8, DSP, LD, lane);
+            block_product<TS>(G1, G1, t >= 2 ? G2 : nullptr, G2, false, true, warp, lane, LD, [&](int i8, int j8, double c0, double c1) {
                 W[(8 * j8 + fc) * LD + 8 * i8 + fr] = c0;
                 W[(8 * j8 + fc + 1) * LD + 8 * i8 + fr] = c1;
-            }
+            });
             __syncthreads();
 #pragma unroll
             for (int y = 0; y < TS; ++y)
