@@ -91,6 +91,6 @@ if __name__ == "__main__":
     rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(PROF, exist_ok=True)
     launches(rnd)
-    for cap in ("prof_fbf_tc", "prof_fbf_simt", "prof_traj_dtw", "prof_traj", "prof_dtw", "prof_dtwbarrier", "prof_argmax", "prof_group", "prof_recheck", "prof_pair", "prof_dtwpipe"):
+    for cap in ("prof_fbf_tc", "prof_fbf_simt", "prof_traj_dtw", "prof_traj", "prof_dtw", "prof_dtwbarrier", "prof_argmax", "prof_group", "prof_recheck", "prof_pair", "prof_dtwpipe", "prof_trajtiled"):
         capture(rnd, cap)
     print(sorted(os.listdir(PROF)))
